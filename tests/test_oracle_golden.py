@@ -72,8 +72,8 @@ def test_train_steps(golden_dir, name):
         if i == 0:
             for k, p in rec["param_small_after"].items():
                 g = rec["grad_small"][k]
-                sel = g.abs() > 1e-6          # skip noise-gradient elements (see above)
-                assert ((sd[k] - p).abs() * sel).max() < 2e-5, (name, k)
+                sel = g.abs() > 1e-5          # skip noise-gradient elements (see above)
+                assert ((sd[k] - p).abs() * sel).max() < 1e-4, (name, k)
 
 
 @pytest.mark.parametrize("name", ["infer_c80.pt", "infer_c80_t512.pt"])
