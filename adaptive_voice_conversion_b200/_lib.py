@@ -1,0 +1,134 @@
+"""ctypes binding of libavc_b200.so (the C ABI declared in include/avc_b200.h).
+
+There is no CPU fallback: if the shared library is missing and cannot be built, importing
+a symbol raises.  ``AVC_LIB`` can point at an explicit .so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("AVC_LIB", os.path.join(_PKG, "libavc_b200.so"))
+
+PAD_REFLECT, PAD_ZERO = 0, 1
+RES_NONE, RES_SAME, RES_POOL, RES_UP = 0, 1, 2, 3
+PACK_FWD, PACK_DGRAD = 0, 1
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
+
+_fp = C.c_void_p  # device pointers travel as integers
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32), ("K", C.c_int32),
+        ("stride", C.c_int32), ("pad_left", C.c_int32), ("pad_mode", C.c_int32), ("in_ups", C.c_int32),
+        ("Tin", C.c_int32), ("Tout", C.c_int32),
+        ("in_", _fp), ("in_bstride", C.c_int64),
+        ("w_packed", _fp), ("w_ld", C.c_int32),
+        ("bias", _fp),
+        ("out", _fp), ("out_bstride", C.c_int64),
+        ("shuffle", C.c_int32), ("norm", C.c_int32), ("eps", C.c_float), ("relu", C.c_int32),
+        ("cond", _fp), ("cond_bstride", C.c_int64),
+        ("res", _fp), ("res_bstride", C.c_int64), ("res_mode", C.c_int32), ("res_T", C.c_int32),
+        ("mask", _fp), ("mask_bstride", C.c_int64),
+        ("save_c", _fp), ("stats", _fp),
+        ("dy", _fp), ("dy_bstride", C.c_int64),
+        ("dc", _fp), ("dcond", _fp), ("dcond_bstride", C.c_int64), ("dbias", _fp),
+    ]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32), ("K", C.c_int32),
+        ("stride", C.c_int32), ("pad_left", C.c_int32), ("Tin", C.c_int32), ("Tout", C.c_int32),
+        ("x", _fp), ("x_bstride", C.c_int64),
+        ("dc", _fp), ("dc_bstride", C.c_int64),
+        ("dw", _fp),
+    ]
+
+
+class FoldDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("C", C.c_int32), ("Tin", C.c_int32), ("pad_left", C.c_int32), ("pad_right", C.c_int32),
+        ("dxp", _fp), ("dres", _fp), ("dres_bstride", C.c_int64),
+        ("res_mode", C.c_int32), ("res_T", C.c_int32),
+        ("dx", _fp), ("dx_bstride", C.c_int64),
+    ]
+
+
+class LinearDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("relu", C.c_int32),
+        ("x", _fp), ("x_bstride", C.c_int64),
+        ("w", _fp), ("bias", _fp), ("res", _fp), ("y_act", _fp),
+        ("out", _fp), ("out_bstride", C.c_int64),
+        ("dy", _fp), ("dy_bstride", C.c_int64),
+        ("dx_add", _fp), ("dx", _fp), ("dw", _fp), ("db", _fp),
+    ]
+
+
+# name -> (restype, argtypes); the single source of truth for tests/test_cabi_symbols.py
+_i, _i64, _p = C.c_int, C.c_int64, C.c_void_p
+PROTOTYPES = {
+    "avc_conv_block_fwd": (_i, [C.POINTER(ConvDesc), _p]),
+    "avc_norm_apply_fwd": (_i, [C.POINTER(ConvDesc), _p]),
+    "avc_norm_bwd": (_i, [C.POINTER(ConvDesc), _p]),
+    "avc_conv_wgrad": (_i, [C.POINTER(WgradDesc), _p]),
+    "avc_fold_add_fwd": (_i, [C.POINTER(FoldDesc), _p]),
+    "avc_pack_conv_weight": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "avc_pack_a4": (_i, [_p, _p, _i64, _i, _i, _i, _p]),
+    "avc_unpack_a4": (_i, [_p, _i64, _p, _i, _i, _i, _p]),
+    "avc_bias_grad": (_i, [_p, _i64, _p, _i, _i, _i, _p]),
+    "avc_time_mean_fwd": (_i, [_p, _i64, _p, _i, _i, _i, _p]),
+    "avc_time_mean_bwd": (_i, [_p, _p, _i64, _i, _i, _i, _p]),
+    "avc_linear_fwd": (_i, [C.POINTER(LinearDesc), _p]),
+    "avc_linear_bwd": (_i, [C.POINTER(LinearDesc), _p]),
+    "avc_reparam_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "avc_reparam_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "avc_vae_loss": (_i, [_p, _p, _i64, _p, _p, _i64, _p, _p, _p, _p, _p, _p]),
+    "avc_sqnorm": (_i, [_p, _i64, _p, _p, _p]),
+    "avc_adam_step": (_i, [_p, _p, _p, _p, _p, _i64, _p, _p, _p, _p]),
+    "avc_fill_zero": (_i, [_p, _i64, _p]),
+    "avc_last_error": (C.c_char_p, []),
+    "avc_build_info": (C.c_char_p, []),
+    "avc_launch_count": (_i64, []),
+}
+
+_lib = None
+
+
+class AvcError(RuntimeError):
+    pass
+
+
+def load(build_if_missing: bool = True):
+    """Load (building first if necessary) the shared library; raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise AvcError(f"{LIB_PATH} is missing (run `python -m adaptive_voice_conversion_b200.build`); there is no CPU fallback")
+        from . import build as _build
+        _build.build()
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().avc_last_error().decode()
+
+
+def check(rc: int, what: str = ""):
+    if rc != OK:
+        raise AvcError(f"{what}: rc={rc}: {last_error()}")
+
+
+def launch_count() -> int:
+    return int(load().avc_launch_count())

@@ -1,0 +1,466 @@
+"""Host-side sequencing of the sm_100a kernels for the AdaIN-VC stacks.
+
+This is the layer between the reference-shaped Python API (model.AE, solver.Solver) and
+the C ABI (include/avc_b200.h).  It mirrors, launch by launch, what the reference's
+SpeakerEncoder / ContentEncoder / Decoder ``forward`` methods do with torch.nn modules
+(model.py:265-277, 301-323, 347-371) and what autograd does for them in
+``loss.backward()`` (solver.py:90) -- but every arithmetic op is one of our kernels, and
+the backward is written out by hand (no autograd inside).
+
+Tensors inside the engine are "A4" activations ([B][C/4][T][4], see avc_b200.h); PyTorch
+only provides device memory (torch.empty) and the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib as L
+
+IN_EPS = 1e-5
+
+
+class A4:
+    """A [B][C/4][T][4] fp32 activation, possibly a channel sub-range of a wider buffer."""
+    __slots__ = ("t", "ptr", "B", "C", "T", "bstride")
+
+    def __init__(self, t, ptr, B, C, T, bstride):
+        self.t, self.ptr, self.B, self.C, self.T, self.bstride = t, ptr, B, C, T, bstride
+
+    @staticmethod
+    def empty(B, C, T, device):
+        assert C % 4 == 0, f"A4 layout needs C % 4 == 0, got {C}"
+        t = torch.empty((B, C // 4, T, 4), dtype=torch.float32, device=device)
+        return A4(t, t.data_ptr(), B, C, T, C * T)
+
+    def channels(self, c0, c1):
+        assert c0 % 4 == 0 and c1 % 4 == 0
+        return A4(self.t, self.ptr + (c0 // 4) * self.T * 16, self.B, c1 - c0, self.T, self.bstride)
+
+    def to_planar(self):  # test/debug helper (torch ops, not on the product path)
+        v = self.t if self.t.shape[1] * 4 == self.C else None
+        assert v is not None, "to_planar only on whole tensors"
+        return v.permute(0, 1, 3, 2).reshape(self.B, self.C, self.T).contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def conv_geometry(K: int, stride: int, Tin: int):
+    pl = K // 2
+    pr = K // 2 - 1 if K % 2 == 0 else K // 2
+    Tout = (Tin + pl + pr - K) // stride + 1
+    return pl, pr, Tout
+
+
+class Engine:
+    """Launch sequencer for one AE configuration on one device."""
+
+    def __init__(self, config: dict, device: torch.device):
+        self.cfg = config
+        self.dev = torch.device(device)
+        if self.dev.type != "cuda":
+            raise L.AvcError("adaptive_voice_conversion_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        self.lib = L.load()
+        self.packed: Dict[str, Dict[str, torch.Tensor]] = {}
+        self._packed_key = None
+        se, ce, de = config["SpeakerEncoder"], config["ContentEncoder"], config["Decoder"]
+        for c in (se, ce):
+            if c.get("act", "relu") != "relu" or c.get("dropout_rate", 0) != 0:
+                raise L.AvcError("only act='relu', dropout_rate=0 (the reference config.yaml) are implemented")
+        if de.get("act", "relu") != "relu" or de.get("dropout_rate", 0) != 0 or de.get("sn", False):
+            raise L.AvcError("Decoder: only act='relu', dropout_rate=0, sn=False are implemented")
+        for up in de["upsample"]:
+            if up not in (1, 2):
+                raise L.AvcError("Decoder.upsample entries must be 1 or 2")
+        for c in (se, ce):
+            for s in c["subsample"]:
+                if s not in (1, 2):
+                    raise L.AvcError("subsample entries must be 1 or 2")
+
+    # ------------------------------------------------------------------ utilities
+    @property
+    def stream(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise L.AvcError(f"{what}: rc={rc}: {L.last_error()}")
+
+    def empty(self, *shape):
+        return torch.empty(shape, dtype=torch.float32, device=self.dev)
+
+    def zeros(self, *shape):
+        t = self.empty(*shape)
+        self._ck(self.lib.avc_fill_zero(t.data_ptr(), t.numel() * 4, self.stream), "fill_zero")
+        return t
+
+    def pack_a4(self, planar: torch.Tensor, dst: A4):
+        B, Cc, T = planar.shape
+        assert planar.is_contiguous() and planar.dtype == torch.float32
+        self._ck(self.lib.avc_pack_a4(planar.data_ptr(), dst.ptr, dst.bstride, B, Cc, T, self.stream), "pack_a4")
+
+    def unpack_a4(self, src: A4, planar: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if planar is None:
+            planar = self.empty(src.B, src.C, src.T)
+        self._ck(self.lib.avc_unpack_a4(src.ptr, src.bstride, planar.data_ptr(), src.B, src.C, src.T, self.stream), "unpack_a4")
+        return planar
+
+    # ------------------------------------------------------------------ weights
+    def conv_names(self) -> List[str]:
+        se, ce, de = self.cfg["SpeakerEncoder"], self.cfg["ContentEncoder"], self.cfg["Decoder"]
+        names = []
+        for enc, c in (("speaker_encoder", se), ("content_encoder", ce)):
+            nb = len(range(c["bank_scale"], c["bank_size"] + 1, c["bank_scale"]))
+            names += [f"{enc}.conv_bank.{i}" for i in range(nb)]
+            names.append(f"{enc}.in_conv_layer")
+            names += [f"{enc}.first_conv_layers.{l}" for l in range(c["n_conv_blocks"])]
+            names += [f"{enc}.second_conv_layers.{l}" for l in range(c["n_conv_blocks"])]
+        names += ["content_encoder.mean_layer", "content_encoder.std_layer", "decoder.in_conv_layer"]
+        names += [f"decoder.first_conv_layers.{l}" for l in range(de["n_conv_blocks"])]
+        names += [f"decoder.second_conv_layers.{l}" for l in range(de["n_conv_blocks"])]
+        names.append("decoder.out_conv_layer")
+        return names
+
+    def pack_weights(self, P: Dict[str, torch.Tensor], need_dgrad: bool, prefixes=None):
+        """nn.Conv1d weights -> kernel operand layouts (re-run whenever parameters change)."""
+        st = self.stream
+        for name in self.conv_names():
+            if prefixes is not None and not name.startswith(prefixes):
+                continue
+            w = P[name + ".weight"]
+            Cout, Cin, K = w.shape
+            slot = self.packed.setdefault(name, {})
+            if "fwd" not in slot or slot["fwd"].numel() != w.numel():
+                slot["fwd"] = self.empty(w.numel())
+            self._ck(self.lib.avc_pack_conv_weight(w.data_ptr(), slot["fwd"].data_ptr(), Cout, Cin, K, L.PACK_FWD, st), "pack_w")
+            if need_dgrad and ".conv_bank." not in name:  # the bank's input (x) needs no gradient
+                if "dgrad" not in slot or slot["dgrad"].numel() != w.numel():
+                    slot["dgrad"] = self.empty(w.numel())
+                self._ck(self.lib.avc_pack_conv_weight(w.data_ptr(), slot["dgrad"].data_ptr(), Cout, Cin, K, L.PACK_DGRAD, st), "pack_w")
+
+    # ------------------------------------------------------------------ one conv block
+    def conv(self, P, name, xin: A4, *, stride=1, shuffle=False, norm=False, cond=None, relu=False,
+             res: Optional[A4] = None, res_mode=L.RES_NONE, out: Optional[A4] = None, train=False):
+        w = P[name + ".weight"]
+        Cout, Cin, K = w.shape
+        assert Cin == xin.C, (name, Cin, xin.C)
+        pl, pr, Tout = conv_geometry(K, stride, xin.T)
+        B = xin.B
+        Cn, Tn = (Cout // 2, Tout * 2) if shuffle else (Cout, Tout)
+        if out is None:
+            out = A4.empty(B, Cn, Tn, self.dev)
+        assert (out.C, out.T) == (Cn, Tn)
+        need_c = train and (norm or relu)
+        fused = (not norm) or (Tout <= 128) or (Tout <= 256 and K in (1, 5))
+        c = A4.empty(B, Cout, Tout, self.dev) if (need_c or not fused) else None
+        stats = self.empty(B, Cn, 2) if norm else None
+        d = L.ConvDesc()
+        d.B, d.Cin, d.Cout, d.K, d.stride = B, Cin, Cout, K, stride
+        d.pad_left, d.pad_mode, d.in_ups, d.Tin, d.Tout = pl, L.PAD_REFLECT, 1, xin.T, Tout
+        d.in_, d.in_bstride = xin.ptr, xin.bstride
+        d.w_packed, d.w_ld = self.packed[name]["fwd"].data_ptr(), Cout
+        d.bias = P[name + ".bias"].data_ptr()
+        d.eps = IN_EPS
+        if fused:
+            self._fill_epilogue(d, out, shuffle, norm, relu, cond, res, res_mode, stats)
+            d.save_c = c.ptr if c is not None else None
+            self._ck(self.lib.avc_conv_block_fwd(C.byref(d), self.stream), f"conv_block_fwd[{name}]")
+        else:
+            d.out, d.out_bstride = c.ptr, c.bstride
+            self._ck(self.lib.avc_conv_block_fwd(C.byref(d), self.stream), f"conv_block_fwd[{name}]")
+            self._fill_epilogue(d, out, shuffle, norm, relu, cond, res, res_mode, stats)
+            d.save_c = c.ptr
+            self._ck(self.lib.avc_norm_apply_fwd(C.byref(d), self.stream), f"norm_apply_fwd[{name}]")
+            if not need_c:
+                c = None
+        rec = None
+        if train:
+            rec = dict(name=name, xin=xin, c=c, stats=stats, cond=cond, out=out, stride=stride, shuffle=shuffle,
+                       norm=norm, relu=relu, K=K, Cin=Cin, Cout=Cout, Tout=Tout, pl=pl, pr=pr)
+        return out, rec
+
+    @staticmethod
+    def _fill_epilogue(d, out, shuffle, norm, relu, cond, res, res_mode, stats):
+        d.out, d.out_bstride = out.ptr, out.bstride
+        d.shuffle, d.norm, d.relu = int(shuffle), int(norm), int(relu)
+        if cond is not None:
+            d.cond, d.cond_bstride = cond.data_ptr(), cond.stride(0)
+        if res is not None:
+            d.res, d.res_bstride, d.res_mode, d.res_T = res.ptr, res.bstride, res_mode, res.T
+        d.stats = _ptr(stats)
+
+    def conv_bwd(self, P, G, rec, dy: A4, *, need_dx=True, dres: Optional[A4] = None, dres_mode=L.RES_NONE,
+                 dcond: Optional[torch.Tensor] = None, mask: Optional[A4] = None, dx_channels=None) -> Optional[A4]:
+        """Backward of one conv block.  dy: grad w.r.t. the block output *before* the residual
+        add.  Returns grad w.r.t. the block input (+ adjoint of the residual branch `dres`)."""
+        name, xin, B = rec["name"], rec["xin"], rec["xin"].B
+        K, Cin, Cout, Tout, stride = rec["K"], rec["Cin"], rec["Cout"], rec["Tout"], rec["stride"]
+        st = self.stream
+        gb = G[name + ".bias"]
+        if rec["norm"] or rec["relu"]:
+            dc = A4.empty(B, Cout, Tout, self.dev)
+            d = L.ConvDesc()
+            d.B, d.Cin, d.Cout, d.K, d.stride, d.Tin, d.Tout = B, Cin, Cout, K, stride, xin.T, Tout
+            d.in_ups = 1
+            d.shuffle, d.norm, d.relu, d.eps = int(rec["shuffle"]), int(rec["norm"]), int(rec["relu"]), IN_EPS
+            d.save_c, d.stats = rec["c"].ptr, _ptr(rec["stats"])
+            if rec["cond"] is not None:
+                d.cond, d.cond_bstride = rec["cond"].data_ptr(), rec["cond"].stride(0)
+                d.dcond, d.dcond_bstride = dcond.data_ptr(), dcond.stride(0)
+            d.dy, d.dy_bstride = dy.ptr, dy.bstride
+            d.dc, d.dbias = dc.ptr, gb.data_ptr()
+            self._ck(self.lib.avc_norm_bwd(C.byref(d), st), f"norm_bwd[{name}]")
+        else:
+            dc = dy
+            self._ck(self.lib.avc_bias_grad(dc.ptr, dc.bstride, gb.data_ptr(), B, Cout, Tout, st), f"bias_grad[{name}]")
+        wd = L.WgradDesc()
+        wd.B, wd.Cin, wd.Cout, wd.K, wd.stride, wd.pad_left, wd.Tin, wd.Tout = B, Cin, Cout, K, stride, rec["pl"], xin.T, Tout
+        wd.x, wd.x_bstride, wd.dc, wd.dc_bstride = xin.ptr, xin.bstride, dc.ptr, dc.bstride
+        wd.dw = G[name + ".weight"].data_ptr()
+        self._ck(self.lib.avc_conv_wgrad(C.byref(wd), st), f"conv_wgrad[{name}]")
+        if not need_dx:
+            return None
+        # data gradient: full transposed conv (zero pad) then fold the reflect halo back
+        Cdx = Cin if dx_channels is None else dx_channels
+        Lp = xin.T + rec["pl"] + rec["pr"]
+        direct = (K == 1 and stride == 1 and dres is None)
+        dx = A4.empty(B, Cdx, xin.T, self.dev)
+        dxp = dx if direct else A4.empty(B, Cdx, Lp, self.dev)
+        d = L.ConvDesc()
+        d.B, d.Cin, d.Cout, d.K, d.stride = B, Cout, Cdx, K, 1
+        d.pad_left, d.pad_mode, d.in_ups, d.Tin, d.Tout = K - 1, L.PAD_ZERO, stride, Tout, Lp
+        d.in_, d.in_bstride = dc.ptr, dc.bstride
+        d.w_packed, d.w_ld = self.packed[name]["dgrad"].data_ptr(), Cin
+        d.out, d.out_bstride = dxp.ptr, dxp.bstride
+        d.eps = IN_EPS
+        if mask is not None:
+            assert direct
+            d.mask, d.mask_bstride = mask.ptr, mask.bstride
+        self._ck(self.lib.avc_conv_block_fwd(C.byref(d), st), f"conv_dgrad[{name}]")
+        if direct:
+            return dx
+        f = L.FoldDesc()
+        f.B, f.C, f.Tin, f.pad_left, f.pad_right = B, Cdx, xin.T, rec["pl"], rec["pr"]
+        f.dxp = dxp.ptr
+        if dres is not None:
+            f.dres, f.dres_bstride, f.res_mode, f.res_T = dres.ptr, dres.bstride, dres_mode, dres.T
+        f.dx, f.dx_bstride = dx.ptr, dx.bstride
+        self._ck(self.lib.avc_fold_add_fwd(C.byref(f), st), f"fold_add[{name}]")
+        return dx
+
+    # ------------------------------------------------------------------ linear layers
+    def linear(self, P, name, x: torch.Tensor, *, relu=False, res=None, out=None, train=False):
+        w = P[name + ".weight"]
+        N, K = w.shape
+        B = x.shape[0]
+        if out is None:
+            out = self.empty(B, N)
+        y_act = self.empty(B, N) if (train and relu) else None
+        d = L.LinearDesc()
+        d.B, d.N, d.K, d.relu = B, N, K, int(relu)
+        d.x, d.x_bstride = x.data_ptr(), x.stride(0)
+        d.w, d.bias = w.data_ptr(), P[name + ".bias"].data_ptr()
+        d.res, d.y_act = _ptr(res), _ptr(y_act)
+        d.out, d.out_bstride = out.data_ptr(), out.stride(0)
+        self._ck(self.lib.avc_linear_fwd(C.byref(d), self.stream), f"linear_fwd[{name}]")
+        rec = dict(name=name, x=x, y_act=y_act, relu=relu, N=N, K=K) if train else None
+        return out, rec
+
+    def linear_bwd(self, P, G, rec, dy: torch.Tensor, *, dx_add=None, need_dx=True):
+        name = rec["name"]
+        B = rec["x"].shape[0]
+        d = L.LinearDesc()
+        d.B, d.N, d.K, d.relu = B, rec["N"], rec["K"], int(rec["relu"])
+        d.x, d.x_bstride = rec["x"].data_ptr(), rec["x"].stride(0)
+        d.w = P[name + ".weight"].data_ptr()
+        d.y_act = _ptr(rec["y_act"])
+        d.dy, d.dy_bstride = dy.data_ptr(), dy.stride(0)
+        dx = self.empty(B, rec["K"]) if need_dx else None
+        d.dx, d.dx_add = _ptr(dx), _ptr(dx_add)
+        d.dw, d.db = G[name + ".weight"].data_ptr(), G[name + ".bias"].data_ptr()
+        self._ck(self.lib.avc_linear_bwd(C.byref(d), self.stream), f"linear_bwd[{name}]")
+        return dx
+
+    # ------------------------------------------------------------------ encoders
+    def _bank_and_in_conv(self, P, enc, c, x_planar: torch.Tensor, norm: bool, train: bool, ctx: dict):
+        """conv_bank + in_conv_layer (model.py:85-91, 266-269 / 302-307).  The concat is never
+        assembled by a copy: every bank conv writes its channel range of one A4 buffer and
+        x itself is packed straight into the last c_in channels."""
+        B, c_in, T = x_planar.shape
+        ks = list(range(c["bank_scale"], c["bank_size"] + 1, c["bank_scale"]))
+        c_bank = c["c_bank"]
+        ctot = c_bank * len(ks) + c_in
+        cat = A4.empty(B, ctot, T, self.dev)
+        x4 = cat.channels(c_bank * len(ks), ctot)
+        self.pack_a4(x_planar, x4)
+        recs = []
+        for i, _k in enumerate(ks):
+            _, r = self.conv(P, f"{enc}.conv_bank.{i}", x4, relu=True, out=cat.channels(i * c_bank, (i + 1) * c_bank), train=False)
+            recs.append(r)
+        out, rec_in = self.conv(P, f"{enc}.in_conv_layer", cat, norm=norm, relu=True, train=train)
+        if train:
+            ctx["cat"], ctx["x4"], ctx["in"] = cat, x4, rec_in
+            ctx["n_bank"], ctx["c_bank"] = len(ks), c_bank
+        return out
+
+    def _enc_blocks(self, P, enc, c, out: A4, norm: bool, train: bool, ctx: dict):
+        blocks = []
+        for l, s in enumerate(c["subsample"][: c["n_conv_blocks"]]):
+            y, r1 = self.conv(P, f"{enc}.first_conv_layers.{l}", out, norm=norm, relu=True, train=train)
+            new, r2 = self.conv(P, f"{enc}.second_conv_layers.{l}", y, stride=s, norm=norm, relu=True, res=out,
+                                res_mode=L.RES_POOL if s > 1 else L.RES_SAME, train=train)
+            blocks.append((r1, r2, s, out))
+            out = new
+        if train:
+            ctx["blocks"] = blocks
+        return out
+
+    def speaker_fwd(self, P, x_planar: torch.Tensor, train: bool):
+        """SpeakerEncoder.forward (model.py:265-277) -> emb [B, c_out]."""
+        c = self.cfg["SpeakerEncoder"]
+        enc = "speaker_encoder"
+        ctx: dict = {}
+        out = self._bank_and_in_conv(P, enc, c, x_planar, norm=False, train=train, ctx=ctx)
+        out = self._enc_blocks(P, enc, c, out, norm=False, train=train, ctx=ctx)
+        B = out.B
+        pooled = self.empty(B, out.C)
+        self._ck(self.lib.avc_time_mean_fwd(out.ptr, out.bstride, pooled.data_ptr(), B, out.C, out.T, self.stream), "time_mean_fwd")
+        h = pooled
+        dense = []
+        for l in range(c["n_dense_blocks"]):
+            y, r1 = self.linear(P, f"{enc}.first_dense_layers.{l}", h, relu=True, train=train)
+            h, r2 = self.linear(P, f"{enc}.second_dense_layers.{l}", y, relu=True, res=h, train=train)
+            dense.append((r1, r2))
+        emb, r_out = self.linear(P, f"{enc}.output_layer", h, train=train)
+        if train:
+            ctx.update(dense=dense, out_rec=r_out, last=out)
+        return emb, ctx
+
+    def speaker_bwd(self, P, G, ctx, demb: torch.Tensor):
+        c = self.cfg["SpeakerEncoder"]
+        dh = self.linear_bwd(P, G, ctx["out_rec"], demb)
+        for r1, r2 in reversed(ctx["dense"]):
+            dy = self.linear_bwd(P, G, r2, dh)                 # through second layer (+ReLU mask)
+            dh = self.linear_bwd(P, G, r1, dy, dx_add=dh)       # through first layer, + identity branch
+        last = ctx["last"]
+        dout = A4.empty(last.B, last.C, last.T, self.dev)
+        self._ck(self.lib.avc_time_mean_bwd(dh.data_ptr(), dout.ptr, dout.bstride, last.B, last.C, last.T, self.stream), "time_mean_bwd")
+        self._enc_bwd(P, G, "speaker_encoder", c, ctx, dout)
+
+    def content_fwd(self, P, x_planar: torch.Tensor, train: bool):
+        """ContentEncoder.forward (model.py:301-323) -> (mu4, ls4) A4 [B, c_out, T/8]."""
+        c = self.cfg["ContentEncoder"]
+        enc = "content_encoder"
+        ctx: dict = {}
+        out = self._bank_and_in_conv(P, enc, c, x_planar, norm=True, train=train, ctx=ctx)
+        out = self._enc_blocks(P, enc, c, out, norm=True, train=train, ctx=ctx)
+        mu4, r_mu = self.conv(P, f"{enc}.mean_layer", out, train=train)
+        ls4, r_ls = self.conv(P, f"{enc}.std_layer", out, train=train)
+        if train:
+            ctx.update(mu_rec=r_mu, ls_rec=r_ls)
+        return mu4, ls4, ctx
+
+    def content_bwd(self, P, G, ctx, dmu4: A4, dls4: A4):
+        c = self.cfg["ContentEncoder"]
+        d1 = self.conv_bwd(P, G, ctx["mu_rec"], dmu4)
+        d2 = self.conv_bwd(P, G, ctx["ls_rec"], dls4)
+        dout = self._add(d1, d2)
+        self._enc_bwd(P, G, "content_encoder", c, ctx, dout)
+
+    def _add(self, a: A4, b: A4) -> A4:
+        """a + b via the fold kernel (pad 0, residual SAME)."""
+        out = A4.empty(a.B, a.C, a.T, self.dev)
+        f = L.FoldDesc()
+        f.B, f.C, f.Tin, f.pad_left, f.pad_right = a.B, a.C, a.T, 0, 0
+        f.dxp = a.ptr
+        assert a.bstride == a.C * a.T
+        f.dres, f.dres_bstride, f.res_mode, f.res_T = b.ptr, b.bstride, L.RES_SAME, b.T
+        f.dx, f.dx_bstride = out.ptr, out.bstride
+        self._ck(self.lib.avc_fold_add_fwd(C.byref(f), self.stream), "add")
+        return out
+
+    def _enc_bwd(self, P, G, enc, c, ctx, dout: A4):
+        for r1, r2, s, _blk_in in reversed(ctx["blocks"]):
+            dy1 = self.conv_bwd(P, G, r2, dout)
+            dout = self.conv_bwd(P, G, r1, dy1, dres=dout, dres_mode=L.RES_POOL if s > 1 else L.RES_SAME)
+        # in_conv: dgrad only towards the bank outputs (x needs no grad), ReLU mask fused
+        cat, nb, cb = ctx["cat"], ctx["n_bank"], ctx["c_bank"]
+        bank_out = cat.channels(0, nb * cb)
+        dbank = self.conv_bwd(P, G, ctx["in"], dout, mask=bank_out, dx_channels=nb * cb)
+        x4 = ctx["x4"]
+        st = self.stream
+        for i in range(nb):
+            name = f"{enc}.conv_bank.{i}"
+            w = P[name + ".weight"]
+            Cout, Cin, K = w.shape
+            pl, pr, Tout = conv_geometry(K, 1, x4.T)
+            dci = dbank.channels(i * cb, (i + 1) * cb)
+            self._ck(self.lib.avc_bias_grad(dci.ptr, dci.bstride, G[name + ".bias"].data_ptr(), x4.B, Cout, Tout, st), "bias_grad")
+            wd = L.WgradDesc()
+            wd.B, wd.Cin, wd.Cout, wd.K, wd.stride, wd.pad_left, wd.Tin, wd.Tout = x4.B, Cin, Cout, K, 1, pl, x4.T, Tout
+            wd.x, wd.x_bstride, wd.dc, wd.dc_bstride = x4.ptr, x4.bstride, dci.ptr, dci.bstride
+            wd.dw = G[name + ".weight"].data_ptr()
+            self._ck(self.lib.avc_conv_wgrad(C.byref(wd), st), f"conv_wgrad[{name}]")
+
+    # ------------------------------------------------------------------ reparameterisation
+    def reparam_fwd(self, mu4: A4, ls4: A4, eps: Optional[torch.Tensor], want_planar=True):
+        B, Cc, T = mu4.B, mu4.C, mu4.T
+        z4 = A4.empty(B, Cc, T, self.dev)
+        mu = self.empty(B, Cc, T) if want_planar else None
+        ls = self.empty(B, Cc, T) if want_planar else None
+        self._ck(self.lib.avc_reparam_fwd(mu4.ptr, ls4.ptr, _ptr(eps), _ptr(mu), _ptr(ls), z4.ptr, B, Cc, T, self.stream), "reparam_fwd")
+        return mu, ls, z4
+
+    def reparam_bwd(self, dz4: Optional[A4], ls4: A4, eps, dmu_ext, dls_ext):
+        B, Cc, T = ls4.B, ls4.C, ls4.T
+        dmu4, dls4 = A4.empty(B, Cc, T, self.dev), A4.empty(B, Cc, T, self.dev)
+        self._ck(self.lib.avc_reparam_bwd(None if dz4 is None else dz4.ptr, ls4.ptr, _ptr(eps), _ptr(dmu_ext), _ptr(dls_ext),
+                                          dmu4.ptr, dls4.ptr, B, Cc, T, self.stream), "reparam_bwd")
+        return dmu4, dls4
+
+    # ------------------------------------------------------------------ decoder
+    def decoder_fwd(self, P, z4: A4, emb: torch.Tensor, train: bool):
+        """Decoder.forward (model.py:347-371) -> dec4 A4 [B, c_out, 8*T]."""
+        c = self.cfg["Decoder"]
+        dn = "decoder"
+        ctx: dict = {}
+        out, r_in = self.conv(P, f"{dn}.in_conv_layer", z4, norm=True, relu=True, train=train)
+        nblk = c["n_conv_blocks"]
+        # the 2*n AdaIN rows (beta|gamma) of every block: conv_affine_layers (model.py:342-343)
+        ch2 = 2 * c["c_h"]
+        conds = self.empty(z4.B, 2 * nblk, ch2)
+        aff = []
+        for i in range(2 * nblk):
+            _, r = self.linear(P, f"{dn}.conv_affine_layers.{i}", emb, out=conds[:, i], train=train)
+            aff.append(r)
+        blocks = []
+        for l, up in enumerate(c["upsample"][:nblk]):
+            y, r1 = self.conv(P, f"{dn}.first_conv_layers.{l}", out, norm=True, cond=conds[:, 2 * l], relu=True, train=train)
+            new, r2 = self.conv(P, f"{dn}.second_conv_layers.{l}", y, shuffle=(up > 1), norm=True, cond=conds[:, 2 * l + 1],
+                                relu=True, res=out, res_mode=L.RES_UP if up > 1 else L.RES_SAME, train=train)
+            blocks.append((r1, r2, up))
+            out = new
+        dec4, r_out = self.conv(P, f"{dn}.out_conv_layer", out, train=train)
+        if train:
+            ctx.update(in_rec=r_in, aff=aff, blocks=blocks, out_rec=r_out, conds=conds, emb=emb)
+        return dec4, ctx
+
+    def decoder_bwd(self, P, G, ctx, ddec4: A4, need_dz=True):
+        """Returns (dz4, demb)."""
+        c = self.cfg["Decoder"]
+        nblk = c["n_conv_blocks"]
+        dout = self.conv_bwd(P, G, ctx["out_rec"], ddec4)
+        dconds = self.empty(*ctx["conds"].shape)
+        for l in reversed(range(nblk)):
+            r1, r2, up = ctx["blocks"][l]
+            dy1 = self.conv_bwd(P, G, r2, dout, dcond=dconds[:, 2 * l + 1])
+            dout = self.conv_bwd(P, G, r1, dy1, dres=dout, dres_mode=L.RES_UP if up > 1 else L.RES_SAME, dcond=dconds[:, 2 * l])
+        dz4 = self.conv_bwd(P, G, ctx["in_rec"], dout, need_dx=need_dz)
+        demb = None
+        for i, r in enumerate(ctx["aff"]):
+            demb = self.linear_bwd(P, G, r, dconds[:, i], dx_add=demb)
+        return dz4, demb

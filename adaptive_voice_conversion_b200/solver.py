@@ -1,0 +1,123 @@
+"""Solver with the reference's surface (solver.py:16-118): ``Solver(config, args)``,
+``train(n)``, ``ae_step(data, lambda_kl) -> {'loss_rec','loss_kl','grad_norm'}``,
+``save_model`` / ``load_model`` / ``save_config`` / ``build_model`` / ``get_data_loaders``.
+
+What changed underneath: the model is the B200-native ``AE``; one optimizer step is
+``FusedTrainer.step`` (hand-written forward+backward kernels, a single NCCL all-reduce of
+the flat gradient when launched with torchrun, fused clip+Adam(amsgrad)); checkpoints stay
+``<path>.ckpt`` (model state_dict) + ``<path>.opt`` (torch.optim.Adam state_dict format),
+written by rank 0 only.  ``args.data_dir == 'synthetic'`` trains on N(0,1) segments.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import yaml
+
+from .data_utils import PickleDataset, SyntheticSegments, get_data_loader
+from .model import AE
+from .optim import FusedAdam
+from .trainer import FusedTrainer
+from .utils import Logger, cc, infinite_iter, local_device
+
+
+def _dist_info():
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        return torch.distributed.get_rank(), torch.distributed.get_world_size()
+    return 0, 1
+
+
+class Solver(object):
+    def __init__(self, config, args):
+        self.config = config
+        self.args = args
+        self.rank, self.world = _dist_info()
+        if self.rank == 0:
+            print(config)
+            print(args)
+        self.logger = Logger(getattr(args, "logdir", "log/")) if self.rank == 0 else None
+        self.get_data_loaders()
+        self.build_model()
+        if self.rank == 0 and getattr(args, "store_model_path", None):
+            self.save_config()
+        if getattr(args, "load_model", False):
+            self.load_model()
+
+    # ---- checkpoints (solver.py:39-55)
+    def save_model(self, iteration):
+        if self.rank != 0:
+            return
+        torch.save(self.model.state_dict(), f"{self.args.store_model_path}.ckpt")
+        torch.save(self.opt.state_dict(), f"{self.args.store_model_path}.opt")
+
+    def save_config(self):
+        with open(f"{self.args.store_model_path}.config.yaml", "w") as f:
+            yaml.dump(self.config, f)
+        with open(f"{self.args.store_model_path}.args.yaml", "w") as f:
+            yaml.dump(vars(self.args), f)
+
+    def load_model(self):
+        if self.rank == 0:
+            print(f"Load model from {self.args.load_model_path}")
+        dev = local_device()
+        self.model.load_state_dict(torch.load(f"{self.args.load_model_path}.ckpt", map_location=dev))
+        opt_path = f"{self.args.load_model_path}.opt"
+        if os.path.exists(opt_path):
+            self.opt.load_state_dict(torch.load(opt_path, map_location=dev))
+        self.trainer.eng.pack_weights(self.trainer.P, need_dgrad=True)
+
+    # ---- data (solver.py:57-68)
+    def get_data_loaders(self):
+        dl = self.config["data_loader"]
+        data_dir = getattr(self.args, "data_dir", "synthetic")
+        if data_dir in (None, "synthetic"):
+            n_mels = self.config["ContentEncoder"]["c_in"] // dl["frame_size"]
+            self.train_dataset = None
+            self.train_loader = SyntheticSegments(dl["batch_size"], n_mels * dl["frame_size"], dl["segment_size"] // dl["frame_size"],
+                                                  seed=1 + self.rank)
+        else:
+            self.train_dataset = PickleDataset(os.path.join(data_dir, f"{self.args.train_set}.pkl"),
+                                               os.path.join(data_dir, self.args.train_index_file),
+                                               segment_size=dl["segment_size"])
+            self.train_loader = get_data_loader(self.train_dataset, frame_size=dl["frame_size"], batch_size=dl["batch_size"],
+                                                shuffle=dl["shuffle"], num_workers=4, drop_last=False)
+        self.train_iter = infinite_iter(self.train_loader)
+
+    # ---- model + optimizer (solver.py:70-79)
+    def build_model(self):
+        self.model = cc(AE(self.config))
+        if self.world > 1:  # replicas start identical: broadcast rank 0's init
+            for p in self.model.parameters():
+                torch.distributed.broadcast(p.data, src=0)
+        self.model.flatten_parameters()
+        o = self.config["optimizer"]
+        self.opt = FusedAdam(self.model, lr=o["lr"], betas=(o["beta1"], o["beta2"]), amsgrad=o["amsgrad"],
+                             weight_decay=o["weight_decay"], max_norm=o["grad_norm"], world_size=self.world)
+        self.trainer = FusedTrainer(self.model, self.opt, self.config)
+        if self.rank == 0:
+            print(self.model)
+            print(self.opt)
+
+    # ---- one step (solver.py:81-97)
+    def ae_step(self, data, lambda_kl, eps=None):
+        x = data.to(local_device(), non_blocking=True)
+        self.trainer.step(x, lambda_kl, eps=eps)
+        loss_rec, loss_kl, grad_norm = self.trainer.losses()
+        return {"loss_rec": loss_rec, "loss_kl": loss_kl, "grad_norm": grad_norm}
+
+    # ---- loop (solver.py:99-118)
+    def train(self, n_iterations):
+        lam = self.config["lambda"]["lambda_kl"]
+        anneal = self.config["annealing_iters"]
+        for iteration in range(n_iterations):
+            lambda_kl = lam if iteration >= anneal else lam * (iteration + 1) / anneal
+            meta = self.ae_step(next(self.train_iter), lambda_kl)
+            if self.rank == 0:
+                if iteration % self.args.summary_steps == 0:
+                    self.logger.scalars_summary(f"{self.args.tag}/ae_train", meta, iteration)
+                print(f"AE:[{iteration + 1}/{n_iterations}], loss_rec={meta['loss_rec']:.2f}, "
+                      f"loss_kl={meta['loss_kl']:.2f}, lambda={lambda_kl:.1e}     ", end="\r")
+                if (iteration + 1) % self.args.save_steps == 0 or iteration + 1 == n_iterations:
+                    self.save_model(iteration=iteration)
+                    print()

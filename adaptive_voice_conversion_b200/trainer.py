@@ -1,0 +1,125 @@
+"""The fused training step: forward, losses, hand-written backward, gradient all-reduce,
+clip + Adam -- the body of ``Solver.ae_step`` (solver.py:81-97) without autograd.
+
+Data parallelism: one process per GPU, parameters and Adam state
+replicated, each rank steps on its own segments, ONE NCCL all-reduce(SUM) of the flat
+gradient buffer per iteration; the 1/world scale is folded into the clip/Adam kernel so
+the order backward -> all-reduce -> global-norm clip -> Adam matches a single-process
+step on the concatenated batch.
+
+With ``use_graph=True`` the step is captured once into CUDA graphs (static shapes) and
+replayed: graph A = zero-grad + forward + loss + backward, graph B = norm + Adam + weight
+re-pack; the all-reduce runs between them (N>1 only).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib as L
+from .engine import A4, Engine
+from .optim import FusedAdam
+
+
+class FusedTrainer:
+    def __init__(self, model, opt: FusedAdam, config: dict, process_group=None):
+        self.model, self.opt, self.cfg = model, opt, config
+        self.dev = opt.flat_p.device
+        self.eng: Engine = model.engine(self.dev)
+        self.lib = L.load()
+        self.P: Dict[str, torch.Tensor] = dict(model.named_parameters())
+        self.G: Dict[str, torch.Tensor] = opt.named_grad_views(model)
+        self.pg = process_group
+        self.world = opt.world_size
+        self.sums = torch.zeros(2, dtype=torch.float32, device=self.dev)
+        self.n_rec = 1
+        self.n_lat = 1
+        self._graphs = None
+        self._static = None
+        self.launches_per_step = 0
+        self.eng.pack_weights(self.P, need_dgrad=True)
+        self._lambda_kl = None
+        opt.sync_hparams(lambda_rec=float(config["lambda"]["lambda_rec"]), lambda_kl=float(config["lambda"]["lambda_kl"]))
+
+    # ------------------------------------------------------------------ pieces
+    def _fwd_bwd(self, x: torch.Tensor, eps: Optional[torch.Tensor]):
+        eng, P, G, st = self.eng, self.P, self.G, None
+        self.opt.zero_grad()
+        emb, cs = eng.speaker_fwd(P, x, True)
+        mu4, ls4, ce = eng.content_fwd(P, x, True)
+        if eps is None:
+            eps = torch.randn((mu4.B, mu4.C, mu4.T), dtype=torch.float32, device=self.dev)
+        mu, ls, z4 = eng.reparam_fwd(mu4, ls4, eps)
+        dec4, cd = eng.decoder_fwd(P, z4, emb, True)
+        dec = eng.unpack_a4(dec4)
+        ddec, dmu, dls = torch.empty_like(dec), torch.empty_like(mu), torch.empty_like(ls)
+        self.n_rec, self.n_lat = dec.numel(), mu.numel()
+        L.check(self.lib.avc_vae_loss(dec.data_ptr(), x.data_ptr(), dec.numel(), mu.data_ptr(), ls.data_ptr(), mu.numel(),
+                                      self.opt.hp.data_ptr(), self.sums.data_ptr(), ddec.data_ptr(), dmu.data_ptr(),
+                                      dls.data_ptr(), eng.stream), "vae_loss")
+        ddec4 = A4.empty(dec4.B, dec4.C, dec4.T, self.dev)
+        eng.pack_a4(ddec, ddec4)
+        dz4, demb = eng.decoder_bwd(P, G, cd, ddec4)
+        dmu4, dls4 = eng.reparam_bwd(dz4, ls4, eps, dmu, dls)
+        eng.content_bwd(P, G, ce, dmu4, dls4)
+        eng.speaker_bwd(P, G, cs, demb)
+        return mu, ls, emb, dec
+
+    def _allreduce(self):
+        if self.world > 1:
+            torch.distributed.all_reduce(self.opt.flat_g, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+
+    def _update(self):
+        self.opt.step()
+        self.eng.pack_weights(self.P, need_dgrad=True)
+
+    def set_lambda_kl(self, lambda_kl: float):
+        if lambda_kl != self._lambda_kl:
+            self._lambda_kl = lambda_kl
+            self.opt.sync_hparams(lambda_kl=float(lambda_kl))
+
+    # ------------------------------------------------------------------ public
+    def step(self, x: torch.Tensor, lambda_kl: float, eps: Optional[torch.Tensor] = None, return_outputs=False):
+        """One optimizer step on device batch x [B, c_in, T].  Enqueues work only; read
+        ``losses()`` to synchronise."""
+        if not x.is_cuda or x.dtype != torch.float32:
+            raise L.AvcError("FusedTrainer.step: x must be a float32 CUDA tensor")
+        x = x.contiguous()
+        self.set_lambda_kl(lambda_kl)
+        if self._graphs is not None and eps is None and tuple(x.shape) == tuple(self._static.shape):
+            if x.data_ptr() != self._static.data_ptr():
+                self._static.copy_(x, non_blocking=True)
+            self._graphs[0].replay()
+            self._allreduce()
+            self._graphs[1].replay()
+            return None
+        n0 = L.launch_count()
+        outs = self._fwd_bwd(x, eps)
+        self._allreduce()
+        self._update()
+        self.launches_per_step = L.launch_count() - n0
+        return outs if return_outputs else None
+
+    def capture(self, x_example: torch.Tensor, warmup: int = 2):
+        """Capture the step for x_example's shape into CUDA graphs.  Runs `warmup` real
+        (eager) steps first -- they DO update the parameters."""
+        lam = self._lambda_kl if self._lambda_kl is not None else float(self.cfg["lambda"]["lambda_kl"])
+        self._static = x_example.contiguous().clone()
+        for _ in range(warmup):
+            self.step(self._static, lam)
+        torch.cuda.synchronize(self.dev)
+        ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        pool = torch.cuda.graph_pool_handle()
+        with torch.cuda.graph(ga, pool=pool):
+            self._fwd_bwd(self._static, None)
+        with torch.cuda.graph(gb, pool=pool):
+            self._update()
+        self._graphs = (ga, gb)
+        return self._static
+
+    def losses(self):
+        """(loss_rec, loss_kl, grad_norm) as Python floats -- synchronises."""
+        s = self.sums.tolist()
+        gn = float(self.opt.grad_norm().item())
+        return s[0] / self.n_rec, 0.5 * s[1] / self.n_lat, gn

@@ -1,0 +1,206 @@
+/*
+ * avc_b200.h -- C ABI of libavc_b200.so: the sm_100a kernels behind the AdaIN-VC hot path.
+ *
+ * The reference (jjery2243542/adaptive_voice_conversion) has no FFI: its hot path is the
+ * Python class surface model.AE / solver.Solver / inference.Inferencer on top of stock
+ * torch.nn modules.  Each entry point below therefore cites the reference lines (relative
+ * to the reference repo root) whose torch ops it replaces; the Python side
+ * (adaptive_voice_conversion_b200/model.py ...) re-exposes the reference's own class API
+ * on top of these calls through ctypes.  See INTEGRATION.md for the binding.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer owned by the caller
+ *    (PyTorch allocates; the library never allocates or frees device memory);
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *    synchronises, so every call is CUDA-graph capturable;
+ *  - every function returns AVC_OK (0) or a negative AVC_ERR_* code and never throws;
+ *    avc_last_error() returns a static message for the most recent failure on the calling
+ *    thread;
+ *  - activations use the "A4" layout: a logical [B][C][T] fp32 tensor is stored as
+ *    [B][C/4][T][4] (four channels interleaved per time step, C % 4 == 0), so one
+ *    (sample, 4-channel chunk) is a contiguous run of T 16-byte vectors.  The reference's
+ *    boundary tensors (x, dec, mu, log_sigma, eps) stay planar [B][C][T]; avc_pack_a4 /
+ *    avc_unpack_a4 convert.  `*_bstride` is the distance in floats between samples, which
+ *    lets a tensor be a channel sub-range of a wider one (the conv-bank concat).
+ */
+#ifndef AVC_B200_H_
+#define AVC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVC_OK 0
+#define AVC_ERR_INVALID (-1)     /* bad argument (null pointer, C % 4 != 0, ...) */
+#define AVC_ERR_UNSUPPORTED (-2) /* valid request this kernel family does not cover */
+#define AVC_ERR_CUDA (-3)        /* a CUDA runtime call failed; see avc_last_error() */
+
+#define AVC_PAD_REFLECT 0
+#define AVC_PAD_ZERO 1
+
+#define AVC_RES_NONE 0
+#define AVC_RES_SAME 1 /* out += res[t]                                   (model.py:249,368) */
+#define AVC_RES_POOL 2 /* out += avg_pool1d(res, 2, ceil_mode=True)[t]    (model.py:248,319) */
+#define AVC_RES_UP 3   /* out += nearest-upsample-x2(res)[t]              (model.py:61-63,367) */
+
+#define AVC_PACK_FWD 0   /* P[ci][j][co]  = W[co][ci][j]                                   */
+#define AVC_PACK_DGRAD 1 /* P[co][j][ci]  = W[co][ci][K-1-j]  (transposed, tap-flipped)     */
+
+/* One fused conv block: reflect-pad -> Conv1d -> [pixel shuffle] -> [InstanceNorm] ->
+ * [AdaIN affine] -> [ReLU] -> [+ residual] -> [* mask].
+ * Replaces pad_layer (model.py:21-32) + nn.Conv1d + pixel_shuffle_1d (:52-59) +
+ * nn.InstanceNorm1d (:296,341) + append_cond (:77-83) + ReLU + the residual adds with
+ * F.avg_pool1d / upsample (:248-249, :319-320, :366-369) of one ConvBlock.
+ * With pad_mode = ZERO / in_ups = 2 the same kernel computes the data gradient of a conv
+ * (see avc_fold_add_fwd).  The struct is also the argument of avc_norm_apply_fwd,
+ * avc_norm_bwd. */
+typedef struct avc_conv_desc {
+  int32_t B, Cin, Cout, K, stride, pad_left, pad_mode, in_ups;
+  int32_t Tin;  /* stored input length; logical length is Tin * in_ups (zero insertion) */
+  int32_t Tout; /* conv output length */
+  const float* in; /* A4 [B][Cin/4][Tin][4] */
+  int64_t in_bstride;
+  const float* w_packed; /* [Cin][K][w_ld] (avc_pack_conv_weight) */
+  int32_t w_ld;
+  const float* bias; /* [Cout] or null */
+  float* out;        /* A4 [B][Cn/4][Tn][4]; Cn = Cout/(1+shuffle), Tn = Tout*(1+shuffle) */
+  int64_t out_bstride;
+  int32_t shuffle; /* 1: out[b][c][2t+s] = conv[b][2c+s][t] before the norm (model.py:52-59) */
+  int32_t norm;    /* 1: InstanceNorm over Tn per (b, c), biased variance */
+  float eps;
+  int32_t relu;
+  const float* cond; /* AdaIN rows: beta = cond[b*cond_bstride + c], gamma = cond[... + Cn + c]; or null */
+  int64_t cond_bstride;
+  const float* res; /* A4 [B][Cn/4][res_T][4] or null */
+  int64_t res_bstride;
+  int32_t res_mode, res_T;
+  const float* mask; /* A4 like out; out *= (mask > 0); or null */
+  int64_t mask_bstride;
+  float* save_c; /* dense A4 [B][Cout/4][Tout][4] raw conv (+bias) kept for backward; or null */
+  float* stats;  /* [B][Cn][2] = (mean, rstd) when norm; or null */
+  /* ---- backward-only fields (avc_norm_bwd) ---- */
+  const float* dy; /* A4 [B][Cn/4][Tn][4], grad w.r.t. the block output */
+  int64_t dy_bstride;
+  float* dc;    /* dense A4 [B][Cout/4][Tout][4], grad w.r.t. the raw conv output */
+  float* dcond; /* [B][2*Cn] (dbeta | dgamma) rows, dcond_bstride apart; or null */
+  int64_t dcond_bstride;
+  float* dbias; /* [Cout], accumulated with atomics; or null */
+} avc_conv_desc;
+
+/* Fused block forward.  norm=1 needs the whole Tn of a sample inside one CTA tile:
+ * supported for Tout <= 256, otherwise AVC_ERR_UNSUPPORTED -- run it with norm=0, relu=0,
+ * res=null, save_c=out-of-conv and follow with avc_norm_apply_fwd. */
+int avc_conv_block_fwd(const avc_conv_desc* d, void* stream);
+/* Two-pass epilogue for long sequences: reads d->save_c, applies shuffle/norm/AdaIN/ReLU/
+ * residual/mask, writes d->out and d->stats. */
+int avc_norm_apply_fwd(const avc_conv_desc* d, void* stream);
+/* Backward of the epilogue: dy, save_c, stats, cond -> dc, dcond, dbias.
+ * (autograd of InstanceNorm1d + append_cond + ReLU, solver.py:90) */
+int avc_norm_bwd(const avc_conv_desc* d, void* stream);
+
+/* Weight gradient of pad_layer+Conv1d: dW[co][ci][j] += sum_{b,t} dc[b][co][t] *
+ * xpad[b][ci][t*stride + j]  (canonical nn.Conv1d layout, accumulated with atomics into a
+ * zeroed buffer).  x is the conv input A4, dc the dense grad of the raw conv output. */
+typedef struct avc_wgrad_desc {
+  int32_t B, Cin, Cout, K, stride, pad_left, Tin, Tout;
+  const float* x;
+  int64_t x_bstride;
+  const float* dc; /* A4 [B][Cout/4][Tout][4], samples dc_bstride apart */
+  int64_t dc_bstride;
+  float* dw; /* [Cout][Cin][K] */
+} avc_wgrad_desc;
+int avc_conv_wgrad(const avc_wgrad_desc* d, void* stream);
+
+/* Adjoint of the reflect padding + residual adjoint.  dxp is the zero-padded "full"
+ * transposed conv output (length Tin + pad_left + pad_right) produced by
+ * avc_conv_block_fwd with the DGRAD weight pack; this folds the mirrored halo back
+ * (adjoint of F.pad(mode='reflect'), model.py:28-30) and adds the gradient arriving
+ * through the block's residual branch. */
+typedef struct avc_fold_desc {
+  int32_t B, C, Tin, pad_left, pad_right;
+  const float* dxp; /* dense A4 [B][C/4][Tin+pad_left+pad_right][4] */
+  const float* dres; /* A4 grad of the block output the residual fed; or null */
+  int64_t dres_bstride;
+  int32_t res_mode, res_T; /* adjoint of AVC_RES_*: SAME (res_T=Tin), POOL (res_T=ceil(Tin/2)), UP (res_T=2*Tin) */
+  float* dx; /* A4 [B][C/4][Tin][4] */
+  int64_t dx_bstride;
+} avc_fold_desc;
+int avc_fold_add_fwd(const avc_fold_desc* d, void* stream);
+
+/* nn.Conv1d weight [Cout][Cin][K] -> kernel operand layout (AVC_PACK_*). */
+int avc_pack_conv_weight(const float* w, float* packed, int Cout, int Cin, int K, int mode, void* stream);
+
+/* planar [B][C][T] <-> A4.  add != 0 accumulates into dst instead of overwriting. */
+int avc_pack_a4(const float* planar, float* a4, int64_t a4_bstride, int B, int C, int T, void* stream);
+int avc_unpack_a4(const float* a4, int64_t a4_bstride, float* planar, int B, int C, int T, void* stream);
+
+/* sum over (b, t) of an A4 tensor -> out[C] (+=): bias gradient of a conv without epilogue. */
+int avc_bias_grad(const float* dc, int64_t bstride, float* dbias, int B, int C, int T, void* stream);
+
+/* AdaptiveAvgPool1d(1) (model.py:231,273) and its adjoint. */
+int avc_time_mean_fwd(const float* a4, int64_t bstride, float* out /*[B][C]*/, int B, int C, int T, void* stream);
+int avc_time_mean_bwd(const float* dout /*[B][C]*/, float* da4, int64_t bstride, int B, int C, int T, void* stream);
+
+/* nn.Linear (+ReLU, + residual): y_act = act(x W^T + b); out = y_act + res.
+ * (model.py:252-263 dense blocks, :276 output layer, :342-343 AdaIN affine layers) */
+typedef struct avc_linear_desc {
+  int32_t B, N, K, relu;
+  const float* x; /* [B][K] */
+  int64_t x_bstride;
+  const float* w;    /* [N][K] (nn.Linear layout) */
+  const float* bias; /* [N] or null */
+  const float* res;  /* [B][N] dense or null */
+  float* y_act;      /* [B][N] dense: activation output kept for the ReLU mask; or null */
+  float* out;        /* [B][N] rows out_bstride apart */
+  int64_t out_bstride;
+  /* backward */
+  const float* dy; /* [B][N] rows dy_bstride apart */
+  int64_t dy_bstride;
+  const float* dx_add; /* [B][K] dense added to dx; or null */
+  float* dx;           /* [B][K] dense or null */
+  float* dw;           /* [N][K] accumulated (+=) */
+  float* db;           /* [N] accumulated (+=) or null */
+} avc_linear_desc;
+int avc_linear_fwd(const avc_linear_desc* d, void* stream);
+int avc_linear_bwd(const avc_linear_desc* d, void* stream); /* mask = (y_act > 0) when relu */
+
+/* VAE reparameterisation (model.py:383-384) fused with the A4->planar conversion of the
+ * two heads: z = mu + exp(log_sigma/2)*eps (eps null: z = mu, the inference path :389-390). */
+int avc_reparam_fwd(const float* mu4, const float* ls4, const float* eps /*planar or null*/,
+                    float* mu /*planar or null*/, float* ls /*planar or null*/, float* z4,
+                    int B, int C, int T, void* stream);
+/* dmu4 = dz4 + dmu_ext ; dls4 = dz4 * eps * 0.5*exp(ls/2) + dls_ext  (ext planar or null) */
+int avc_reparam_bwd(const float* dz4, const float* ls4, const float* eps, const float* dmu_ext,
+                    const float* dls_ext, float* dmu4, float* dls4, int B, int C, int T, void* stream);
+
+/* Losses of Solver.ae_step (solver.py:84-88) with their gradients in one pass.
+ * hp (device): [0]=lambda_rec [1]=lambda_kl.  sums (device, zeroed by the call):
+ * [0]=sum|dec-x| [1]=sum(exp(ls)+mu^2-1-ls).  d* receive d(lambda_rec*L1 + lambda_kl*KL). */
+int avc_vae_loss(const float* dec, const float* x, int64_t n_rec, const float* mu, const float* ls,
+                 int64_t n_lat, const float* hp, float* sums, float* ddec, float* dmu, float* dls,
+                 void* stream);
+
+/* clip_grad_norm_ + Adam(amsgrad, L2 weight decay) over flat fp32 buffers
+ * (solver.py:91-93, :75-77).  avc_sqnorm writes sum(g^2) to out[0] (deterministic
+ * two-stage reduction; scratch >= 1024 floats).
+ * hp (device): [2]=grad_scale (1/world for DP) [3]=lr [4]=beta1 [5]=beta2 [6]=eps
+ * [7]=weight_decay [8]=max_norm [9]=amsgrad(0/1).  step (device, float) is incremented by
+ * the kernel.  The clip coefficient is min(1, max_norm / (grad_scale*sqrt(sqnorm) + 1e-6)). */
+int avc_sqnorm(const float* g, int64_t n, float* scratch, float* out, void* stream);
+int avc_adam_step(float* p, const float* g, float* m, float* v, float* vmax, int64_t n,
+                  const float* hp, const float* sqnorm, float* step, void* stream);
+
+int avc_fill_zero(void* ptr, int64_t bytes, void* stream);
+
+const char* avc_last_error(void);
+/* "sm_100a" build tag, number of kernels launched so far by this process (for bench.py's
+ * gpu_launches claim). */
+const char* avc_build_info(void);
+int64_t avc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVC_B200_H_ */

@@ -1,0 +1,293 @@
+"""Kernel-level parity (GPU): every C-ABI kernel against the CPU oracle / plain torch fp32
+on the same seeded inputs.  Tolerance: 1e-4 relative to the tensor's max (fp32 FFMA path;
+the north-star budget is 1e-3)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle.ae_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-4
+
+
+def relerr(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from adaptive_voice_conversion_b200.engine import Engine
+    return Engine(orc.default_config(80), torch.device("cuda", 0))
+
+
+def to_a4(eng, x):
+    from adaptive_voice_conversion_b200.engine import A4
+    x = x.cuda().contiguous()
+    a = A4.empty(x.shape[0], x.shape[1], x.shape[2], x.device)
+    eng.pack_a4(x, a)
+    return a
+
+
+def from_a4(eng, a):
+    return eng.unpack_a4(a).cpu()
+
+
+def rnd(shape, seed):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed))
+
+
+def test_pack_unpack_roundtrip(eng):
+    x = rnd((3, 12, 37), 0)
+    a = to_a4(eng, x)
+    assert torch.equal(a.t.cpu(), x.reshape(3, 3, 4, 37).permute(0, 1, 3, 2).contiguous())
+    assert torch.equal(from_a4(eng, a), x)
+
+
+def ref_block(x, w, b, stride, shuffle, norm, cond, relu, res, res_mode):
+    """The reference op sequence of one ConvBlock, via the oracle's primitives (CPU fp32)."""
+    y = orc.reflect_conv1d(x, w, b, stride)
+    if shuffle:
+        y = orc.pixel_shuffle_1d(y, 2)
+    if norm:
+        y = orc.instance_norm(y)
+    if cond is not None:
+        y = orc.adain(y, cond)
+    if relu:
+        y = F.relu(y)
+    if res is not None:
+        if res_mode == 1:
+            y = y + res
+        elif res_mode == 2:
+            y = y + F.avg_pool1d(res, kernel_size=2, ceil_mode=True)
+        else:
+            y = y + F.interpolate(res, scale_factor=2, mode="nearest")
+    return y
+
+
+CASES = [
+    # B, Cin, Cout, K, stride, T, shuffle, norm, cond, relu, res_mode
+    (3, 80, 128, 1, 1, 128, 0, 0, 0, 1, 0),
+    (3, 80, 128, 2, 1, 128, 0, 0, 0, 1, 0),
+    (2, 80, 128, 3, 1, 64, 0, 0, 0, 1, 0),
+    (2, 80, 128, 4, 1, 128, 0, 0, 0, 1, 0),
+    (2, 16, 128, 6, 1, 128, 0, 0, 0, 1, 0),
+    (2, 16, 128, 7, 1, 128, 0, 0, 0, 1, 0),
+    (2, 80, 128, 8, 1, 128, 0, 0, 0, 1, 0),
+    (5, 128, 128, 5, 1, 128, 0, 1, 0, 1, 0),      # content first conv
+    (5, 128, 128, 5, 2, 128, 0, 1, 0, 1, 2),      # content second conv, stride 2, pooled residual
+    (5, 128, 128, 5, 1, 64, 0, 1, 0, 1, 1),
+    (19, 128, 128, 5, 2, 32, 0, 1, 0, 1, 2),      # multi-sample tiles, ragged batch
+    (19, 128, 128, 5, 1, 16, 0, 0, 0, 1, 1),      # speaker block (no norm)
+    (9, 128, 128, 5, 1, 16, 0, 1, 1, 1, 0),       # decoder first conv (AdaIN)
+    (9, 128, 256, 5, 1, 16, 1, 1, 1, 1, 3),       # decoder second conv: shuffle + AdaIN + upsampled residual
+    (3, 128, 256, 5, 1, 64, 1, 1, 1, 1, 3),
+    (3, 128, 128, 5, 1, 128, 0, 1, 1, 1, 1),
+    (2, 1104, 128, 1, 1, 128, 0, 1, 0, 1, 0),     # content in_conv
+    (2, 128, 80, 1, 1, 128, 0, 0, 0, 0, 0),       # out_conv (Cout not a multiple of the tile)
+    (2, 128, 128, 5, 1, 37, 0, 1, 0, 1, 1),       # odd length
+    (2, 128, 128, 5, 2, 37, 0, 1, 0, 1, 2),       # odd length, stride 2, lone pooled tail
+    (2, 128, 128, 5, 1, 200, 0, 1, 0, 1, 1),      # 64x256 tile
+    (2, 128, 128, 5, 2, 400, 0, 1, 0, 1, 2),      # 64x256 tile stride 2
+    (2, 128, 128, 5, 1, 300, 0, 1, 1, 1, 1),      # > 256: two-pass norm
+    (2, 128, 256, 5, 1, 150, 1, 1, 1, 1, 3),      # shuffle -> Tn=300, Tout=150 fused 256 tile
+    (2, 128, 256, 5, 1, 300, 1, 1, 1, 1, 3),      # two-pass norm with shuffle
+    (2, 128, 128, 5, 1, 300, 0, 0, 0, 1, 1),      # tiled, no norm
+    (2, 80, 128, 8, 1, 301, 0, 0, 0, 1, 0),       # tiled bank conv, odd length
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
+def test_conv_block_fwd_bwd(eng, case):
+    from adaptive_voice_conversion_b200 import _lib as L
+    B, Cin, Cout, K, stride, T, shuffle, norm, use_cond, relu, res_mode = case
+    x = rnd((B, Cin, T), 1)
+    w = rnd((Cout, Cin, K), 2) / math.sqrt(Cin * K)
+    b = rnd((Cout,), 3) * 0.1
+    pl, pr, Tout = (K // 2, K // 2 - (1 if K % 2 == 0 else 0), None)
+    Tout = (T + pl + pr - K) // stride + 1
+    Cn, Tn = (Cout // 2, 2 * Tout) if shuffle else (Cout, Tout)
+    cond = (rnd((B, 2 * Cn), 4) * 0.5 + 0.7) if use_cond else None
+    res_T = {0: 0, 1: Tn, 2: T, 3: Tn // 2}[res_mode]
+    res = rnd((B, Cn, res_T), 5) if res_mode else None
+    if res_mode == 2:
+        assert math.ceil(res_T / 2) == Tn
+
+    # ---- reference (CPU, autograd)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    cr = cond.clone().requires_grad_(True) if cond is not None else None
+    rr = res.clone().requires_grad_(True) if res is not None else None
+    yr = ref_block(xr, wr, br, stride, shuffle, norm, cr, relu, rr, res_mode)
+    dy = rnd(tuple(yr.shape), 6)
+    yr.backward(dy)
+
+    # ---- ours
+    P = {"blk.weight": w.cuda(), "blk.bias": b.cuda()}
+    G = {"blk.weight": torch.zeros_like(P["blk.weight"]), "blk.bias": torch.zeros_like(P["blk.bias"])}
+    eng.packed.pop("blk", None)
+    for mode, key in ((L.PACK_FWD, "fwd"), (L.PACK_DGRAD, "dgrad")):
+        t = eng.empty(w.numel())
+        L.check(eng.lib.avc_pack_conv_weight(P["blk.weight"].data_ptr(), t.data_ptr(), Cout, Cin, K, mode, eng.stream), "pack")
+        eng.packed.setdefault("blk", {})[key] = t
+    xa = to_a4(eng, x)
+    ra = to_a4(eng, res) if res is not None else None
+    cg = cond.cuda() if cond is not None else None
+    out, rec = eng.conv(P, "blk", xa, stride=stride, shuffle=bool(shuffle), norm=bool(norm), cond=cg, relu=bool(relu),
+                        res=ra, res_mode=res_mode, train=True)
+    y = from_a4(eng, out)
+    assert y.shape == yr.shape
+    assert relerr(y, yr) < TOL, f"forward {relerr(y, yr)}"
+
+    # inference-mode call (no saved tensors) must give the same result
+    out2, _ = eng.conv(P, "blk", xa, stride=stride, shuffle=bool(shuffle), norm=bool(norm), cond=cg, relu=bool(relu),
+                       res=ra, res_mode=res_mode, train=False)
+    assert torch.equal(from_a4(eng, out2), y)
+
+    dya = to_a4(eng, dy)
+    dcond = torch.zeros_like(cg) if cg is not None else None
+    # residual adjoint is exercised with the *same* dy, as in the real block structure where
+    # the block output's grad feeds both the conv branch and the residual branch:
+    dx = eng.conv_bwd(P, G, rec, dya, dcond=dcond)
+    torch.cuda.synchronize()
+    gtol = 5e-4
+    assert relerr(from_a4(eng, dx), xr.grad) < gtol, f"dx {relerr(from_a4(eng, dx), xr.grad)}"
+    assert relerr(G["blk.weight"], wr.grad) < gtol, f"dW {relerr(G['blk.weight'], wr.grad)}"
+    if norm and not shuffle:
+        assert float(G["blk.bias"].abs().max()) < 1e-3 * float(dy.abs().sum() / Cout + 1)  # analytically zero
+    else:
+        assert relerr(G["blk.bias"], br.grad) < gtol, f"db {relerr(G['blk.bias'], br.grad)}"
+    if cond is not None:
+        assert relerr(dcond, cr.grad) < gtol, f"dcond {relerr(dcond, cr.grad)}"
+
+
+@pytest.mark.parametrize("mode,T", [(1, 64), (2, 64), (2, 37), (3, 32)])
+def test_fold_residual_adjoint(eng, mode, T):
+    """fold_add with pad 0 == adjoint of the residual branch alone."""
+    from adaptive_voice_conversion_b200 import _lib as L
+    from adaptive_voice_conversion_b200.engine import A4
+    import ctypes as C
+    B, Cc = 3, 16
+    prev = rnd((B, Cc, T), 7).requires_grad_(True)
+    if mode == 1:
+        r = prev * 1.0
+    elif mode == 2:
+        r = F.avg_pool1d(prev, 2, ceil_mode=True)
+    else:
+        r = F.interpolate(prev, scale_factor=2, mode="nearest")
+    dout = rnd(tuple(r.shape), 8)
+    r.backward(dout)
+    base = rnd((B, Cc, T), 9)
+    f = L.FoldDesc()
+    a, d = to_a4(eng, base), to_a4(eng, dout)
+    o = A4.empty(B, Cc, T, a.t.device)
+    f.B, f.C, f.Tin, f.pad_left, f.pad_right = B, Cc, T, 0, 0
+    f.dxp, f.dres, f.dres_bstride, f.res_mode, f.res_T = a.ptr, d.ptr, d.bstride, mode, d.T
+    f.dx, f.dx_bstride = o.ptr, o.bstride
+    L.check(eng.lib.avc_fold_add_fwd(C.byref(f), eng.stream), "fold")
+    assert relerr(from_a4(eng, o), base + prev.grad) < 1e-6
+
+
+def test_linear_fwd_bwd(eng):
+    B, K, N = 37, 128, 256
+    x, w, b, res = rnd((B, K), 1), rnd((N, K), 2) / math.sqrt(K), rnd((N,), 3), rnd((B, N), 4)
+    xr, wr, br, rr = [t.clone().requires_grad_(True) for t in (x, w, b, res)]
+    yr = F.relu(F.linear(xr, wr, br)) + rr
+    dy = rnd((B, N), 5)
+    yr.backward(dy)
+    P = {"l.weight": w.cuda(), "l.bias": b.cuda()}
+    G = {k: torch.zeros_like(v) for k, v in P.items()}
+    out, rec = eng.linear(P, "l", x.cuda(), relu=True, res=res.cuda(), train=True)
+    assert relerr(out, yr) < TOL
+    add = rnd((B, K), 6)
+    dx = eng.linear_bwd(P, G, rec, dy.cuda(), dx_add=add.cuda())
+    assert relerr(dx, xr.grad + add) < TOL
+    assert relerr(G["l.weight"], wr.grad) < TOL
+    assert relerr(G["l.bias"], br.grad) < TOL
+
+
+def test_time_mean(eng):
+    x = rnd((5, 128, 16), 1)
+    a = to_a4(eng, x)
+    out = eng.empty(5, 128)
+    eng._ck(eng.lib.avc_time_mean_fwd(a.ptr, a.bstride, out.data_ptr(), 5, 128, 16, eng.stream), "tm")
+    assert relerr(out, x.mean(2)) < 1e-6
+    from adaptive_voice_conversion_b200.engine import A4
+    d = A4.empty(5, 128, 16, out.device)
+    g = rnd((5, 128), 2).cuda()
+    eng._ck(eng.lib.avc_time_mean_bwd(g.data_ptr(), d.ptr, d.bstride, 5, 128, 16, eng.stream), "tmb")
+    assert relerr(from_a4(eng, d), (g.cpu() / 16)[:, :, None].expand(5, 128, 16)) < 1e-6
+
+
+def test_reparam_and_loss(eng):
+    B, Cc, T = 4, 128, 16
+    mu, ls, eps = rnd((B, Cc, T), 1), rnd((B, Cc, T), 2) * 0.3, rnd((B, Cc, T), 3)
+    mur, lsr = mu.clone().requires_grad_(True), ls.clone().requires_grad_(True)
+    z = mur + torch.exp(lsr / 2) * eps
+    dz = rnd((B, Cc, T), 4)
+    kl = 0.5 * torch.mean(torch.exp(lsr) + mur ** 2 - 1 - lsr)
+    (0.7 * kl + (z * dz).sum()).backward()
+    mu4, ls4 = to_a4(eng, mu), to_a4(eng, ls)
+    m2, l2, z4 = eng.reparam_fwd(mu4, ls4, eps.cuda())
+    assert torch.equal(m2.cpu(), mu) and torch.equal(l2.cpu(), ls)
+    assert relerr(from_a4(eng, z4), z) < 1e-6
+    # loss kernel
+    from adaptive_voice_conversion_b200 import _lib as L
+    dec, x = rnd((B, 80, 128), 5), rnd((B, 80, 128), 6)
+    dec[0, 0, :4] = x[0, 0, :4]  # exact zeros: sign(0) = 0
+    decr = dec.clone().requires_grad_(True)
+    l1 = (decr - x).abs().mean()
+    (10 * l1).backward()
+    hp = torch.zeros(16)
+    hp[0], hp[1] = 10.0, 0.7
+    hp = hp.cuda()
+    sums = eng.empty(2)
+    dg, xg, mg, lg = dec.cuda(), x.cuda(), mu.cuda(), ls.cuda()
+    ddec, dmu, dls = torch.empty_like(dg), torch.empty_like(mg), torch.empty_like(lg)
+    L.check(eng.lib.avc_vae_loss(dg.data_ptr(), xg.data_ptr(), dg.numel(), mg.data_ptr(), lg.data_ptr(), mg.numel(),
+                                 hp.data_ptr(), sums.data_ptr(), ddec.data_ptr(), dmu.data_ptr(), dls.data_ptr(), eng.stream), "loss")
+    s = sums.cpu()
+    assert abs(float(s[0]) / dec.numel() - float(l1)) / float(l1) < 1e-5
+    assert abs(0.5 * float(s[1]) / mu.numel() - float(kl)) / float(kl) < 1e-5
+    assert relerr(ddec, decr.grad) < 1e-6
+    dmu4, dls4 = eng.reparam_bwd(to_a4(eng, dz), ls4, eps.cuda(), dmu, dls)
+    assert relerr(from_a4(eng, dmu4), mur.grad) < 1e-5
+    assert relerr(from_a4(eng, dls4), lsr.grad) < 1e-5
+
+
+def test_adam_matches_torch(eng):
+    """avc_sqnorm + avc_adam_step vs clip_grad_norm_ + torch.optim.Adam(amsgrad, wd) over 3 steps."""
+    from adaptive_voice_conversion_b200 import _lib as L
+    n = 100003
+    p0 = rnd((n,), 1)
+    pr = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pr], lr=5e-4, betas=(0.9, 0.999), amsgrad=True, weight_decay=1e-4)
+    p = p0.cuda()
+    m, v, vm = torch.zeros_like(p), torch.zeros_like(p), torch.zeros_like(p)
+    hp = torch.tensor([10, 1, 0.5, 5e-4, 0.9, 0.999, 1e-8, 1e-4, 5.0, 1.0] + [0] * 6, dtype=torch.float32).cuda()
+    step, sq, scratch = torch.zeros(1).cuda(), torch.zeros(1).cuda(), torch.zeros(1024).cuda()
+    for it in range(3):
+        g = rnd((n,), 10 + it) * (0.05 if it == 1 else 0.001)  # it==1 exceeds max_norm -> clipping active
+        pr.grad = g.clone()
+        gn = torch.nn.utils.clip_grad_norm_([pr], max_norm=5.0)
+        opt.step()
+        g2 = (g * 2).cuda()  # world=2 style: summed grads, grad_scale 0.5
+        L.check(eng.lib.avc_sqnorm(g2.data_ptr(), n, scratch.data_ptr(), sq.data_ptr(), eng.stream), "sq")
+        L.check(eng.lib.avc_adam_step(p.data_ptr(), g2.data_ptr(), m.data_ptr(), v.data_ptr(), vm.data_ptr(), n,
+                                      hp.data_ptr(), sq.data_ptr(), step.data_ptr(), eng.stream), "adam")
+        assert abs(0.5 * math.sqrt(float(sq)) - float(gn)) / float(gn) < 1e-5
+        assert float((p.cpu() - pr.detach()).abs().max()) < 2e-6, it
+    assert float(step) == 3.0
+
+
+def test_errors_are_reported(eng):
+    from adaptive_voice_conversion_b200 import _lib as L
+    import ctypes as C
+    d = L.ConvDesc()
+    assert eng.lib.avc_conv_block_fwd(C.byref(d), eng.stream) == L.ERR_INVALID
+    assert "non-positive" in L.last_error() or "null" in L.last_error()
+    x = torch.zeros(1, 6, 8).cuda()
+    assert eng.lib.avc_pack_a4(x.data_ptr(), x.data_ptr(), 48, 1, 6, 8, eng.stream) == L.ERR_INVALID  # C % 4 != 0

@@ -1,0 +1,62 @@
+"""CPU: host-side logic that does not need a device."""
+import pytest
+import torch
+
+import oracle.ae_oracle as orc
+
+
+def test_conv_geometry_matches_torch():
+    from adaptive_voice_conversion_b200.engine import conv_geometry
+    for K in range(1, 9):
+        for stride in (1, 2):
+            for T in (8, 16, 37, 128, 301):
+                pl, pr, Tout = conv_geometry(K, stride, T)
+                w = torch.zeros(1, 1, K)
+                y = orc.reflect_conv1d(torch.zeros(1, 1, T), w, None, stride)
+                assert Tout == y.shape[-1] and pl + pr == K - 1
+
+
+def test_model_state_dict_matches_reference_inventory():
+    from adaptive_voice_conversion_b200.model import AE
+    for c_in in (80, 512):
+        cfg = orc.default_config(c_in)
+        m = AE(cfg)
+        sd = m.state_dict()
+        assert [(k, tuple(v.shape)) for k, v in sd.items()] == [(k, tuple(s)) for k, s in orc.param_shapes(cfg)]
+
+
+def test_no_cpu_fallback():
+    from adaptive_voice_conversion_b200 import _lib as L
+    from adaptive_voice_conversion_b200.model import AE
+    m = AE(orc.default_config(80))
+    with pytest.raises(L.AvcError):
+        m(torch.zeros(1, 80, 128))
+    with pytest.raises(L.AvcError):
+        m.inference(torch.zeros(1, 80, 128), torch.zeros(1, 80, 128))
+    if not torch.cuda.is_available():
+        from adaptive_voice_conversion_b200.engine import Engine
+        with pytest.raises(L.AvcError):
+            Engine(orc.default_config(80), torch.device("cpu"))
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under the package may reference it."""
+    import os
+    from conftest import ROOT
+    pkg = os.path.join(ROOT, "adaptive_voice_conversion_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_collate_and_synthetic_loader():
+    import numpy as np
+    from adaptive_voice_conversion_b200.data_utils import CollateFn, SyntheticSegments
+    items = [np.arange(128 * 80, dtype=np.float32).reshape(128, 80) for _ in range(3)]
+    out = CollateFn(1)(items)
+    assert out.shape == (3, 80, 128) and float(out[0, 5, 7]) == 7 * 80 + 5
+    it = iter(SyntheticSegments(4, 80, 128, seed=3))
+    a, b = next(it), next(it)
+    assert a.shape == (4, 80, 128) and not torch.equal(a, b)
