@@ -107,11 +107,14 @@ def load(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        if not build_if_missing:
-            raise AvcError(f"{LIB_PATH} is missing (run `python -m adaptive_voice_conversion_b200.build`); there is no CPU fallback")
+    if "AVC_LIB" not in os.environ:
+        # stamp-checked: a no-op when libavc_b200.so matches the sources, a rebuild when a
+        # .cu/.cuh/.h changed, an error when it is stale and nvcc is unavailable
         from . import build as _build
-        _build.build()
+        if build_if_missing or os.path.exists(LIB_PATH):
+            _build.build(allow_build=build_if_missing)
+    if not os.path.exists(LIB_PATH):
+        raise AvcError(f"{LIB_PATH} is missing (run `python -m adaptive_voice_conversion_b200.build`); there is no CPU fallback")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol

@@ -36,7 +36,7 @@ def _digest(paths) -> str:
     h = hashlib.sha256()
     for p in sorted(paths):
         with open(p, "rb") as f:
-            h.update(p.encode())
+            h.update(os.path.basename(p).encode())  # location independent: the tree moves to the GPU box
             h.update(f.read())
     h.update(" ".join(ARCH + FLAGS).encode())
     return h.hexdigest()
@@ -52,12 +52,14 @@ def headers():
     return hs
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, allow_build: bool = True) -> str:
     os.makedirs(OBJ, exist_ok=True)
     stamp = os.path.join(OBJ, "stamp.txt")
     dig = _digest(sources() + headers())
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB
+    if not allow_build:
+        raise RuntimeError(f"{LIB} is missing or older than its sources and building was not allowed")
     cc = nvcc()
     hdr_dig = _digest(headers())
 

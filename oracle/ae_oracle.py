@@ -301,3 +301,28 @@ def init_state(config: dict, seed: int = 0) -> State:
             bound = 1.0 / math.sqrt(fan_in)
         sd[name] = (torch.rand(shape, generator=g) * 2 - 1) * bound
     return sd
+
+
+class TorchOptimStep:
+    """Solver.ae_step exactly as the reference drives it (solver.py:81-93): the oracle's
+    functional forward, ``loss.backward()``, ``clip_grad_norm_`` and the stock
+    ``torch.optim.Adam(amsgrad, weight_decay)``.  This is the CPU leg ``bench.py`` times
+    (stock torch kernels end to end, like the reference) and a second opinion for
+    ``clip_and_adam``."""
+
+    def __init__(self, sd: State, config: dict):
+        self.config = config
+        self.params = {k: torch.nn.Parameter(v.detach().clone()) for k, v in sd.items()}
+        o = config["optimizer"]
+        self.opt = torch.optim.Adam(list(self.params.values()), lr=o["lr"], betas=(o["beta1"], o["beta2"]),
+                                    amsgrad=o["amsgrad"], weight_decay=o["weight_decay"])
+
+    def step(self, x: Tensor, eps: Tensor, lambda_kl: float) -> dict:
+        mu, log_sigma, emb, dec = ae_forward(self.params, self.config, x, eps)
+        loss_rec, loss_kl = ae_losses(x, mu, log_sigma, dec)
+        loss = self.config["lambda"]["lambda_rec"] * loss_rec + lambda_kl * loss_kl
+        self.opt.zero_grad()
+        loss.backward()
+        gn = torch.nn.utils.clip_grad_norm_(list(self.params.values()), max_norm=self.config["optimizer"]["grad_norm"])
+        self.opt.step()
+        return {"loss_rec": float(loss_rec.detach()), "loss_kl": float(loss_kl.detach()), "grad_norm": float(gn)}

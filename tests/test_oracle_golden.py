@@ -102,3 +102,18 @@ def test_live_reference_matches_fixture(golden_dir):
     torch.manual_seed(100)
     mu, ls, emb, dec = ae(fx["x"])
     assert rel(dec, fx["steps"][0]["dec"]) < 1e-5
+
+
+def test_torch_optim_step_agrees_with_restated_adam(golden_dir):
+    """The two CPU step drivers of the oracle (hand-restated clip+Adam vs stock torch.optim)
+    agree on the first step."""
+    fx = load(golden_dir, "train_c80_b1.pt")
+    cfg = orc.default_config(80)
+    sd = orc.init_state(cfg, seed=0)
+    stepper = orc.TorchOptimStep(sd, cfg)
+    eps = fx["steps"][0]["eps"]
+    m = stepper.step(fx["x"], eps, fx["lambda_kl"])
+    res = orc.ae_train_step(sd, orc.AdamState(sd), cfg, fx["x"], eps, fx["lambda_kl"])
+    assert abs(m["grad_norm"] - res["grad_norm"]) / res["grad_norm"] < 1e-5
+    worst = max(float((stepper.params[k].detach() - sd[k]).abs().max()) for k in sd)
+    assert worst < 1e-6
