@@ -66,6 +66,7 @@ class Engine:
             raise L.AvcError("adaptive_voice_conversion_b200 runs on CUDA (sm_100a) only; there is no CPU path")
         self.lib = L.load()
         self.packed: Dict[str, Dict[str, torch.Tensor]] = {}
+        self.debug = None  # optional callback(name, stage, obj) for tools/diag_*.py
         self._packed_key = None
         se, ce, de = config["SpeakerEncoder"], config["ContentEncoder"], config["Decoder"]
         for c in (se, ce):
@@ -214,6 +215,8 @@ class Engine:
             d.dy, d.dy_bstride = dy.ptr, dy.bstride
             d.dc, d.dbias = dc.ptr, gb.data_ptr()
             self._ck(self.lib.avc_norm_bwd(C.byref(d), st), f"norm_bwd[{name}]")
+            if self.debug:
+                self.debug(name, "dc", dc)
         else:
             dc = dy
             self._ck(self.lib.avc_bias_grad(dc.ptr, dc.bstride, gb.data_ptr(), B, Cout, Tout, st), f"bias_grad[{name}]")
@@ -222,6 +225,8 @@ class Engine:
         wd.x, wd.x_bstride, wd.dc, wd.dc_bstride = xin.ptr, xin.bstride, dc.ptr, dc.bstride
         wd.dw = G[name + ".weight"].data_ptr()
         self._ck(self.lib.avc_conv_wgrad(C.byref(wd), st), f"conv_wgrad[{name}]")
+        if self.debug:
+            self.debug(name, "dw", G[name + ".weight"])
         if not need_dx:
             return None
         # data gradient: full transposed conv (zero pad) then fold the reflect halo back
@@ -250,6 +255,9 @@ class Engine:
             f.dres, f.dres_bstride, f.res_mode, f.res_T = dres.ptr, dres.bstride, dres_mode, dres.T
         f.dx, f.dx_bstride = dx.ptr, dx.bstride
         self._ck(self.lib.avc_fold_add_fwd(C.byref(f), st), f"fold_add[{name}]")
+        if self.debug:
+            self.debug(name, "dxp", dxp)
+            self.debug(name, "dx", dx)
         return dx
 
     # ------------------------------------------------------------------ linear layers
