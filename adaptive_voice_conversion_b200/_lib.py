@@ -35,6 +35,7 @@ class ConvDesc(C.Structure):
         ("save_c", _fp), ("stats", _fp),
         ("dy", _fp), ("dy_bstride", C.c_int64),
         ("dc", _fp), ("dcond", _fp), ("dcond_bstride", C.c_int64), ("dbias", _fp),
+        ("w_tc", _fp),
     ]
 
 
@@ -72,6 +73,9 @@ class LinearDesc(C.Structure):
 _i, _i64, _p = C.c_int, C.c_int64, C.c_void_p
 PROTOTYPES = {
     "avc_conv_block_fwd": (_i, [C.POINTER(ConvDesc), _p]),
+    "avc_conv_block_tc": (_i, [C.POINTER(ConvDesc), _p, _p]),
+    "avc_pack_conv_weight_tc": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "avc_tc_packed_floats": (_i64, [_i, _i, _i]),
     "avc_norm_apply_fwd": (_i, [C.POINTER(ConvDesc), _p]),
     "avc_norm_bwd": (_i, [C.POINTER(ConvDesc), _p]),
     "avc_conv_wgrad": (_i, [C.POINTER(WgradDesc), _p]),

@@ -1,0 +1,333 @@
+// Fused ConvBlock forward on the 5th-gen tensor cores (tcgen05, TF32 inputs / fp32 accumulate).
+//
+// Same contract as conv_simt.cu (reflect/zero pad -> Conv1d -> [pixel shuffle] ->
+// [InstanceNorm] -> [AdaIN] -> [ReLU] -> [+residual] -> [*mask]); replaces the same reference
+// ops (model.py:21-32, 52-59, 77-83, 237-250, 309-320, 354-369) and, with the DGRAD pack and
+// zero padding, autograd's conv data gradient.
+//
+// Formulation (no im2col): per sample, D[co][t] = sum_tap sum_ci W_tap[co][ci] * X[ci][t+tap].
+//   * A operand = weights of one tap, K-major [ci/4][co][4] (no swizzle): 128 co rows x 16 ci.
+//   * B operand = the input tile in its HBM layout [ci/4][row][4] staged ONCE per 16-channel
+//     slab; the taps are the same tile at descriptor start + tap*16 bytes (row shift), so one
+//     staged tile feeds all K taps.  Reflect / zero halos are patched in shared memory.
+//   * D = 128 lanes (co) x Npad columns (time) per sample in TMEM; G samples per CTA share every
+//     weight stage.  Epilogue: thread <-> lane <-> output channel, so the InstanceNorm
+//     statistics of a (sample, channel) are a per-thread reduction over TMEM columns.
+// Pipeline: warp 0 = bulk-copy (TMA) producer, warps 1+3 = halo patch + round-to-nearest TF32
+// of the staged inputs (the tensor core truncates; rounding here keeps the path unbiased),
+// warp 2 = MMA issuer; all four warps run the epilogue (one TMEM lane quarter each).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace avc {
+
+int validate_conv_desc(const avc_conv_desc* d, const char* who);
+
+constexpr int TC_SLAB = 16;          // input channels per pipeline stage (2 MMA K-steps)
+constexpr int TC_WTAP_BYTES = 8192;  // one tap of one slab: 4 chunks x 128 co x 16 B
+constexpr int TC_MAX_STAGES = 4;
+
+struct TcArgs {
+  avc_conv_desc d;
+  int G, npad, rows, nslab, nstage, ncols;  // samples/CTA, padded cols/sample, smem rows/sample, Cin/16, ring depth, TMEM cols
+  uint32_t stage_bytes, w_bytes;
+  int* status;
+};
+
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(128, 1) conv_block_tc_kernel(const TcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_full[TC_MAX_STAGES], bar_ready[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_done;
+  __shared__ uint32_t tmem_slot;
+  const avc_conv_desc& d = a.d;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b0 = blockIdx.x * a.G;
+  const int mtile = blockIdx.y;
+  const int nsamp = min(a.G, d.B - b0);
+  const int K = d.K;
+  const int xrows = a.G * a.rows;                 // rows of one chunk plane in a stage
+  const uint32_t x_chunk_bytes = (uint32_t)xrows * 16u;
+
+  if (tid == 0) {
+    for (int s = 0; s < a.nstage; ++s) {
+      tc::mbar_init(&bar_full[s], 1);
+      tc::mbar_init(&bar_ready[s], 64);
+      tc::mbar_init(&bar_empty[s], 1);
+    }
+    tc::mbar_init(&bar_done, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, (uint32_t)a.ncols);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  bool ok = true;
+
+  // ------------------------------------------------------------------ main loop (warp roles)
+  if (warp == 0) {
+    if (lane == 0) {
+      const float* wsrc = d.w_tc + (size_t)mtile * a.nslab * (a.w_bytes / 4);
+      for (int i = 0; i < a.nslab && ok; ++i) {
+        const int s = i % a.nstage;
+        const uint32_t ph = (uint32_t)(i / a.nstage) & 1u;
+        if (i >= a.nstage) ok = tc::mbar_wait(&bar_empty[s], ph ^ 1u, a.status, 2);
+        if (!ok) break;
+        uint8_t* sw = smem + (size_t)s * a.stage_bytes;
+        uint8_t* sx = sw + a.w_bytes;
+        tc::mbar_arrive_expect_tx(&bar_full[s], a.w_bytes + (uint32_t)nsamp * 4u * (uint32_t)d.Tin * 16u);
+        tc::bulk_g2s(sw, wsrc + (size_t)i * (a.w_bytes / 4), a.w_bytes, &bar_full[s]);
+        for (int g = 0; g < nsamp; ++g)
+          for (int q = 0; q < 4; ++q)
+            tc::bulk_g2s(sx + (size_t)q * x_chunk_bytes + ((size_t)g * a.rows + d.pad_left) * 16,
+                         d.in + (size_t)(b0 + g) * d.in_bstride + ((size_t)(i * 4 + q) * d.Tin) * 4, (uint32_t)d.Tin * 16u, &bar_full[s]);
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_tf32(128, a.npad, 0, 0);
+      for (int i = 0; i < a.nslab && ok; ++i) {
+        const int s = i % a.nstage;
+        const uint32_t ph = (uint32_t)(i / a.nstage) & 1u;
+        ok = tc::mbar_wait(&bar_ready[s], ph, a.status, 3);
+        if (!ok) break;
+        tc::tc_fence_after();
+        const uint32_t sw = tc::smem_u32(smem + (size_t)s * a.stage_bytes);
+        const uint32_t sx = sw + a.w_bytes;
+        for (int j = 0; j < K; ++j)
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t ad = tc::make_sdesc(sw + j * TC_WTAP_BYTES + ks * 4096, 2048, 128);
+            for (int g = 0; g < nsamp; ++g) {
+              const uint64_t bd = tc::make_sdesc(sx + ks * 2 * x_chunk_bytes + (uint32_t)(g * a.rows + j) * 16u, x_chunk_bytes, 128);
+              tc::mma_tf32(tbase + (uint32_t)(g * a.npad), ad, bd, idesc, (i | j | ks) ? 1u : 0u);
+            }
+          }
+        tc::mma_commit(&bar_empty[s]);
+      }
+      if (ok) tc::mma_commit(&bar_done);
+    }
+  } else {
+    // warps 1 and 3: round staged inputs to TF32 (RN) and patch the halo rows
+    const int ptid = (warp == 1 ? 0 : 32) + lane;  // 0..63
+    for (int i = 0; i < a.nslab && ok; ++i) {
+      const int s = i % a.nstage;
+      const uint32_t ph = (uint32_t)(i / a.nstage) & 1u;
+      ok = tc::mbar_wait(&bar_full[s], ph, a.status, 4);
+      if (!ok) break;
+      float4* sx = reinterpret_cast<float4*>(smem + (size_t)s * a.stage_bytes + a.w_bytes);
+      // data rows: round in place
+      const int per = nsamp * d.Tin;
+      for (int idx = ptid; idx < 4 * per; idx += 64) {
+        const int q = idx / per, r = idx - q * per;
+        const int g = r / d.Tin, t = r - g * d.Tin;
+        float4* p = sx + (size_t)q * xrows + g * a.rows + d.pad_left + t;
+        float4 v = *p;
+        v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+        *p = v;
+      }
+      __syncwarp();
+      // warps 1 and 3 touch disjoint (q,g,row) sets above only by index striding, so the halo
+      // rows (copies of rounded data rows) need both warps' rounding to be complete:
+      asm volatile("bar.sync 1, 64;" ::: "memory");
+      const int halo = a.rows - d.Tin;  // rows that are not data (left pad + right pad + slack)
+      for (int idx = ptid; idx < 4 * nsamp * halo; idx += 64) {
+        const int q = idx / (nsamp * halo), r = idx - q * (nsamp * halo);
+        const int g = r / halo, h = r - g * halo;
+        const int u = h < d.pad_left ? h : d.Tin + h;  // row index within the sample's segment
+        const int p = src_pos(u - d.pad_left, d.Tin, d.pad_mode, 1);
+        float4* base = sx + (size_t)q * xrows + g * a.rows;
+        base[u] = (p >= 0) ? base[d.pad_left + p] : zero4();
+      }
+      tc::fence_proxy_async_smem();
+      tc::mbar_arrive(&bar_ready[s]);
+    }
+  }
+
+  // ------------------------------------------------------------------ epilogue (all warps)
+  __syncwarp();
+  ok = tc::mbar_wait(&bar_done, 0, a.status, 5) && ok;
+  ok = __syncthreads_and(ok) != 0;  // block-uniform: the TMEM loads below are .sync.aligned
+  tc::tc_fence_after();
+  const int co = mtile * 128 + tid;  // conv output row of this thread
+  const bool co_ok = co < d.Cout;
+  if (ok) {
+    const float bias = (d.bias && co_ok) ? __ldg(d.bias + co) : 0.f;
+    const int shuf = d.shuffle;
+    const int Cn = shuf ? d.Cout / 2 : d.Cout;
+    const int Tn = shuf ? d.Tout * 2 : d.Tout;
+    const int cn = shuf ? co >> 1 : co;  // normalized channel
+    const int sx_ = shuf ? (co & 1) : 0;
+    const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
+    for (int g = 0; g < nsamp; ++g) {
+      const int b = b0 + g;
+      float mean = 0.f, rstd = 1.f;
+      if (d.norm) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int c0 = 0; c0 < a.npad; c0 += 16) {
+          float v[16];
+          tc::tmem_ld16(lane_addr + (uint32_t)(g * a.npad + c0), v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (c0 + i < d.Tout) {
+              const float x = v[i] + bias;
+              s1 += x;
+              s2 = fmaf(x, x, s2);
+            }
+        }
+        if (shuf) {  // rows (2c, 2c+1) pool into normalized channel c
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+        }
+        const float inv = 1.f / (float)Tn;
+        mean = s1 * inv;
+        const float var = fmaxf(s2 * inv - mean * mean, 0.f);
+        rstd = rsqrtf(var + d.eps);
+        if (d.stats && co_ok && sx_ == 0) {
+          d.stats[((size_t)b * Cn + cn) * 2 + 0] = mean;
+          d.stats[((size_t)b * Cn + cn) * 2 + 1] = rstd;
+        }
+      }
+      float beta = 0.f, gamma = 1.f;
+      if (d.cond && co_ok) {
+        beta = __ldg(d.cond + (size_t)b * d.cond_bstride + cn);
+        gamma = __ldg(d.cond + (size_t)b * d.cond_bstride + Cn + cn);
+      }
+      float* outp = d.out + (size_t)b * d.out_bstride + ((size_t)(cn >> 2) * Tn) * 4 + (cn & 3);
+      float* cp = d.save_c ? d.save_c + (((size_t)b * (d.Cout >> 2) + (co >> 2)) * d.Tout) * 4 + (co & 3) : nullptr;
+      const float* resp = d.res ? d.res + (size_t)b * d.res_bstride + ((size_t)(cn >> 2) * d.res_T) * 4 + (cn & 3) : nullptr;
+      const float* maskp = d.mask ? d.mask + (size_t)b * d.mask_bstride + ((size_t)(cn >> 2) * Tn) * 4 + (cn & 3) : nullptr;
+      for (int c0 = 0; c0 < a.npad; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(lane_addr + (uint32_t)(g * a.npad + c0), v);
+        if (!co_ok) continue;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int t = c0 + i;
+          if (t >= d.Tout) continue;
+          float x = v[i] + bias;
+          if (cp) cp[(size_t)t * 4] = x;
+          const int tn = shuf ? 2 * t + sx_ : t;
+          if (d.norm) x = (x - mean) * rstd;
+          x = fmaf(x, gamma, beta);
+          if (d.relu) x = fmaxf(x, 0.f);
+          if (resp) {
+            float r;
+            if (d.res_mode == AVC_RES_SAME) r = __ldg(resp + (size_t)tn * 4);
+            else if (d.res_mode == AVC_RES_UP) r = __ldg(resp + (size_t)(tn >> 1) * 4);
+            else {
+              r = __ldg(resp + (size_t)(2 * tn) * 4);
+              if (2 * tn + 1 < d.res_T) r = 0.5f * (r + __ldg(resp + (size_t)(2 * tn + 1) * 4));
+            }
+            x += r;
+          }
+          if (maskp && !(__ldg(maskp + (size_t)tn * 4) > 0.f)) x = 0.f;
+          outp[(size_t)tn * 4] = x;
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tbase, (uint32_t)a.ncols);
+}
+
+// nn.Conv1d weight [Cout][Cin][K] -> per (m-tile, 16-channel slab) blocks
+// [tap][chunk 4][co 128][4 floats], TF32-rounded, zero padded: one contiguous bulk copy per stage.
+__global__ void pack_weight_tc_kernel(const float* __restrict__ w, float* __restrict__ p, int Cout, int Cin, int K, int mode,
+                                      int co_total, int ci_total) {
+  // mode FWD: conv(co', ci', j) = W[co'][ci'][j];  DGRAD: conv(co', ci', j) = W[ci'][co'][K-1-j]
+  // co_total / ci_total: channel counts of the conv being packed (FWD: Cout/Cin, DGRAD: Cin/Cout)
+  const int mt = (co_total + 127) / 128, nslab = (ci_total + TC_SLAB - 1) / TC_SLAB;
+  const int64_t n = (int64_t)mt * nslab * K * 4 * 128 * 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int e = (int)(r % 4); r /= 4;
+    const int col = (int)(r % 128); r /= 128;
+    const int q = (int)(r % 4); r /= 4;
+    const int j = (int)(r % K); r /= K;
+    const int sl = (int)(r % nslab); r /= nslab;
+    const int m = (int)r;
+    const int co = m * 128 + col, ci = sl * TC_SLAB + q * 4 + e;
+    float v = 0.f;
+    if (co < co_total && ci < ci_total)
+      v = (mode == AVC_PACK_FWD) ? __ldg(w + ((int64_t)co * Cin + ci) * K + j) : __ldg(w + ((int64_t)ci * Cin + co) * K + (K - 1 - j));
+    p[i] = round_tf32(v);
+  }
+}
+
+}  // namespace avc
+
+using namespace avc;
+
+extern "C" int64_t avc_tc_packed_floats(int co_total, int ci_total, int K) {
+  return (int64_t)((co_total + 127) / 128) * ((ci_total + TC_SLAB - 1) / TC_SLAB) * K * 4 * 128 * 4;
+}
+
+extern "C" int avc_pack_conv_weight_tc(const float* w, float* packed, int Cout, int Cin, int K, int mode, void* stream) {
+  AVC_REQUIRE(w && packed && Cout > 0 && Cin > 0 && K > 0, AVC_ERR_INVALID, "avc_pack_conv_weight_tc: bad argument");
+  AVC_REQUIRE(mode == AVC_PACK_FWD || mode == AVC_PACK_DGRAD, AVC_ERR_INVALID, "avc_pack_conv_weight_tc: bad mode");
+  const int co_total = mode == AVC_PACK_FWD ? Cout : Cin, ci_total = mode == AVC_PACK_FWD ? Cin : Cout;
+  const int64_t n = avc_tc_packed_floats(co_total, ci_total, K);
+  int blocks = (int)cdiv64(n, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  pack_weight_tc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, packed, Cout, Cin, K, mode, co_total, ci_total);
+  AVC_CHECK_LAUNCH("pack_conv_weight_tc");
+  return AVC_OK;
+}
+
+extern "C" int avc_conv_block_tc(const avc_conv_desc* d, int* status, void* stream) {
+  int rc = validate_conv_desc(d, "avc_conv_block_tc");
+  if (rc != AVC_OK) return rc;
+  AVC_REQUIRE(d->in && d->w_tc && d->out && status, AVC_ERR_INVALID, "avc_conv_block_tc: null in/w_tc/out/status");
+  AVC_REQUIRE(d->stride == 1 && d->in_ups == 1, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: stride/in_ups must be 1");
+  AVC_REQUIRE(d->K >= 1 && d->K <= 8, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: K=%d not in 1..8", d->K);
+  AVC_REQUIRE(d->Cin % TC_SLAB == 0, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: Cin %% 16 != 0");
+  AVC_REQUIRE(d->Tout <= 256, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: Tout > 256");
+  AVC_REQUIRE(d->Tout <= d->Tin + d->K - 1, AVC_ERR_INVALID, "avc_conv_block_tc: Tout too large for Tin");
+  AVC_REQUIRE(!d->res || d->res_mode != AVC_RES_NONE, AVC_ERR_INVALID, "avc_conv_block_tc: res without res_mode");
+  TcArgs a;
+  a.d = *d;
+  if (!a.d.res) a.d.res_mode = AVC_RES_NONE;
+  a.status = status;
+  a.npad = (d->Tout + 15) / 16 * 16;
+  a.rows = a.npad + d->K - 1;
+  if (a.rows < d->Tin + d->pad_left) a.rows = d->Tin + d->pad_left;  // all data rows must fit
+  a.nslab = d->Cin / TC_SLAB;
+  a.w_bytes = (uint32_t)d->K * TC_WTAP_BYTES;
+  const int mtiles = cdiv(d->Cout, 128);
+  int G = cdiv(d->B * mtiles, 148);
+  const int gmax_tmem = 512 / a.npad;
+  if (G > gmax_tmem) G = gmax_tmem;
+  if (G < 1) G = 1;
+  const int smem_max = 220 * 1024;
+  auto stage_bytes = [&](int g) { return (uint32_t)(a.w_bytes + 4 * g * a.rows * 16); };
+  while (G > 1 && 2 * stage_bytes(G) > (uint32_t)smem_max) --G;
+  AVC_REQUIRE(2 * stage_bytes(G) <= (uint32_t)smem_max, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: tile does not fit shared memory");
+  a.G = G;
+  a.stage_bytes = (stage_bytes(G) + 1023) / 1024 * 1024;
+  a.nstage = smem_max / (int)a.stage_bytes;
+  if (a.nstage > TC_MAX_STAGES) a.nstage = TC_MAX_STAGES;
+  if (a.nstage > a.nslab) a.nstage = a.nslab;
+  int ncols = 32;
+  while (ncols < G * a.npad) ncols <<= 1;
+  a.ncols = ncols;
+  const int smem = a.nstage * (int)a.stage_bytes;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(conv_block_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (e != cudaSuccess) {
+      set_error("avc_conv_block_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return AVC_ERR_CUDA;
+    }
+    attr_smem = smem_max;
+  }
+  dim3 grid(cdiv(d->B, G), mtiles);
+  conv_block_tc_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(a);
+  AVC_CHECK_LAUNCH("conv_block_tc");
+  return AVC_OK;
+}

@@ -13,6 +13,7 @@ only provides device memory (torch.empty) and the current CUDA stream.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -67,6 +68,12 @@ class Engine:
         self.lib = L.load()
         self.packed: Dict[str, Dict[str, torch.Tensor]] = {}
         self.debug = None  # optional callback(name, stage, obj) for tools/diag_*.py
+        # "tf32": conv blocks / data gradients on the tcgen05 tensor cores (TF32 inputs rounded
+        # to nearest, fp32 accumulate); "fp32": the exact FFMA kernels.  AVC_PRECISION overrides.
+        self.precision = os.environ.get("AVC_PRECISION", "tf32")
+        if self.precision not in ("tf32", "fp32"):
+            raise L.AvcError("AVC_PRECISION must be 'tf32' or 'fp32'")
+        self.tc_status = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self._packed_key = None
         se, ce, de = config["SpeakerEncoder"], config["ContentEncoder"], config["Decoder"]
         for c in (se, ce):
@@ -93,6 +100,12 @@ class Engine:
 
     def empty(self, *shape):
         return torch.empty(shape, dtype=torch.float32, device=self.dev)
+
+    def check_tc_status(self):
+        """Synchronises; raises if a tcgen05 pipeline barrier ever timed out."""
+        code = int(self.tc_status.item())
+        if code != 0:
+            raise L.AvcError(f"tcgen05 conv pipeline barrier timed out (code {code})")
 
     def zeros(self, *shape):
         t = self.empty(*shape)
@@ -138,10 +151,19 @@ class Engine:
             if "fwd" not in slot or slot["fwd"].numel() != w.numel():
                 slot["fwd"] = self.empty(w.numel())
             self._ck(self.lib.avc_pack_conv_weight(w.data_ptr(), slot["fwd"].data_ptr(), Cout, Cin, K, L.PACK_FWD, st), "pack_w")
-            if need_dgrad and ".conv_bank." not in name:  # the bank's input (x) needs no gradient
+            want_dgrad = need_dgrad and ".conv_bank." not in name  # the bank's input (x) needs no gradient
+            if want_dgrad:
                 if "dgrad" not in slot or slot["dgrad"].numel() != w.numel():
                     slot["dgrad"] = self.empty(w.numel())
                 self._ck(self.lib.avc_pack_conv_weight(w.data_ptr(), slot["dgrad"].data_ptr(), Cout, Cin, K, L.PACK_DGRAD, st), "pack_w")
+            if self.precision == "tf32":
+                for key, mode, co_t, ci_t, want in (("fwd_tc", L.PACK_FWD, Cout, Cin, True), ("dgrad_tc", L.PACK_DGRAD, Cin, Cout, want_dgrad)):
+                    if not want or ci_t % 16 != 0:
+                        continue
+                    n = int(self.lib.avc_tc_packed_floats(co_t, ci_t, K))
+                    if key not in slot or slot[key].numel() != n:
+                        slot[key] = self.empty(n)
+                    self._ck(self.lib.avc_pack_conv_weight_tc(w.data_ptr(), slot[key].data_ptr(), Cout, Cin, K, mode, st), "pack_w_tc")
 
     # ------------------------------------------------------------------ one conv block
     def conv(self, P, name, xin: A4, *, stride=1, shuffle=False, norm=False, cond=None, relu=False,
@@ -156,7 +178,8 @@ class Engine:
             out = A4.empty(B, Cn, Tn, self.dev)
         assert (out.C, out.T) == (Cn, Tn)
         need_c = train and (norm or relu)
-        fused = (not norm) or (Tout <= 128) or (Tout <= 256 and K in (1, 5))
+        use_tc = (self.precision == "tf32" and stride == 1 and Cin % 16 == 0 and Tout <= 256 and "fwd_tc" in self.packed[name])
+        fused = use_tc or (not norm) or (Tout <= 128) or (Tout <= 256 and K in (1, 5))
         c = A4.empty(B, Cout, Tout, self.dev) if (need_c or not fused) else None
         stats = self.empty(B, Cn, 2) if norm else None
         d = L.ConvDesc()
@@ -169,7 +192,11 @@ class Engine:
         if fused:
             self._fill_epilogue(d, out, shuffle, norm, relu, cond, res, res_mode, stats)
             d.save_c = c.ptr if c is not None else None
-            self._ck(self.lib.avc_conv_block_fwd(C.byref(d), self.stream), f"conv_block_fwd[{name}]")
+            if use_tc:
+                d.w_tc = self.packed[name]["fwd_tc"].data_ptr()
+                self._ck(self.lib.avc_conv_block_tc(C.byref(d), self.tc_status.data_ptr(), self.stream), f"conv_block_tc[{name}]")
+            else:
+                self._ck(self.lib.avc_conv_block_fwd(C.byref(d), self.stream), f"conv_block_fwd[{name}]")
         else:
             d.out, d.out_bstride = c.ptr, c.bstride
             self._ck(self.lib.avc_conv_block_fwd(C.byref(d), self.stream), f"conv_block_fwd[{name}]")
@@ -245,7 +272,11 @@ class Engine:
         if mask is not None:
             assert direct
             d.mask, d.mask_bstride = mask.ptr, mask.bstride
-        self._ck(self.lib.avc_conv_block_fwd(C.byref(d), st), f"conv_dgrad[{name}]")
+        if (self.precision == "tf32" and stride == 1 and Cout % 16 == 0 and Lp <= 256 and "dgrad_tc" in self.packed[name]):
+            d.w_tc = self.packed[name]["dgrad_tc"].data_ptr()
+            self._ck(self.lib.avc_conv_block_tc(C.byref(d), self.tc_status.data_ptr(), st), f"conv_dgrad_tc[{name}]")
+        else:
+            self._ck(self.lib.avc_conv_block_fwd(C.byref(d), st), f"conv_dgrad[{name}]")
         if direct:
             return dx
         f = L.FoldDesc()

@@ -87,12 +87,24 @@ typedef struct avc_conv_desc {
   float* dcond; /* [B][2*Cn] (dbeta | dgamma) rows, dcond_bstride apart; or null */
   int64_t dcond_bstride;
   float* dbias; /* [Cout], accumulated with atomics; or null */
+  /* ---- tensor-core path (avc_conv_block_tc) ---- */
+  const float* w_tc; /* weights packed by avc_pack_conv_weight_tc; or null */
 } avc_conv_desc;
 
 /* Fused block forward.  norm=1 needs the whole Tn of a sample inside one CTA tile:
  * supported for Tout <= 256, otherwise AVC_ERR_UNSUPPORTED -- run it with norm=0, relu=0,
  * res=null, save_c=out-of-conv and follow with avc_norm_apply_fwd. */
 int avc_conv_block_fwd(const avc_conv_desc* d, void* stream);
+/* The same fused block on the tcgen05 tensor cores (TF32 inputs rounded to nearest, fp32
+ * accumulation in TMEM).  Covers stride 1, in_ups 1, Cin % 16 == 0, Tout <= 256; otherwise
+ * AVC_ERR_UNSUPPORTED (use avc_conv_block_fwd).  Reads d->w_tc instead of d->w_packed.
+ * status: device int, set non-zero if an internal pipeline barrier timed out. */
+int avc_conv_block_tc(const avc_conv_desc* d, int* status, void* stream);
+/* nn.Conv1d weight [Cout][Cin][K] -> tcgen05 operand blocks (TF32-rounded), AVC_PACK_FWD or
+ * AVC_PACK_DGRAD; avc_tc_packed_floats gives the buffer size for a conv with co_total output
+ * and ci_total input channels (FWD: Cout, Cin; DGRAD: Cin, Cout). */
+int avc_pack_conv_weight_tc(const float* w, float* packed, int Cout, int Cin, int K, int mode, void* stream);
+int64_t avc_tc_packed_floats(int co_total, int ci_total, int K);
 /* Two-pass epilogue for long sequences: reads d->save_c, applies shuffle/norm/AdaIN/ReLU/
  * residual/mask, writes d->out and d->stats. */
 int avc_norm_apply_fwd(const avc_conv_desc* d, void* stream);

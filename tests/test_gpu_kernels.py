@@ -22,7 +22,9 @@ def relerr(a, b):
 @pytest.fixture(scope="module")
 def eng():
     from adaptive_voice_conversion_b200.engine import Engine
-    return Engine(orc.default_config(80), torch.device("cuda", 0))
+    e = Engine(orc.default_config(80), torch.device("cuda", 0))
+    e.precision = "fp32"   # this file pins the exact-fp32 FFMA kernels; tests/test_gpu_tc_conv.py covers tcgen05
+    return e
 
 
 def to_a4(eng, x):

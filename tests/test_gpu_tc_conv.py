@@ -1,0 +1,82 @@
+"""GPU: the tcgen05 (TF32) fused conv block and its data-gradient use against the CPU oracle.
+TF32 inputs are rounded to nearest (10-bit mantissa): tolerance 3e-3 of the tensor max for a
+single block (fp32 path: 2e-4, tests/test_gpu_kernels.py)."""
+import math
+
+import pytest
+import torch
+
+import oracle.ae_oracle as orc
+from test_gpu_kernels import ref_block, relerr, rnd, to_a4, from_a4
+
+pytestmark = pytest.mark.gpu
+TOL = 3e-3
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from adaptive_voice_conversion_b200.engine import Engine
+    e = Engine(orc.default_config(80), torch.device("cuda", 0))
+    e.precision = "tf32"
+    return e
+
+
+CASES = [
+    # B, Cin, Cout, K, T, shuffle, norm, cond, relu, res_mode
+    (5, 128, 128, 5, 128, 0, 1, 0, 1, 0),
+    (5, 128, 128, 5, 64, 0, 1, 0, 1, 1),
+    (19, 128, 128, 5, 16, 0, 0, 0, 1, 1),
+    (300, 128, 128, 5, 16, 0, 1, 1, 1, 0),    # several samples per CTA, ragged tail
+    (9, 128, 256, 5, 16, 1, 1, 1, 1, 3),      # pixel shuffle: two M tiles
+    (3, 128, 256, 5, 64, 1, 1, 1, 1, 3),
+    (3, 80, 128, 8, 128, 0, 0, 0, 1, 0),      # bank conv, even kernel
+    (3, 80, 128, 1, 128, 0, 0, 0, 1, 0),
+    (3, 80, 128, 3, 128, 0, 0, 0, 1, 0),
+    (2, 1104, 128, 1, 128, 0, 1, 0, 1, 0),    # in_conv: 69 slabs through the ring
+    (2, 128, 80, 1, 128, 0, 0, 0, 0, 0),      # out_conv: partial M tile
+    (2, 128, 128, 5, 37, 0, 1, 0, 1, 1),      # odd length
+    (2, 128, 128, 5, 200, 0, 1, 0, 1, 1),     # N = 208 columns
+    (2, 128, 128, 5, 256, 0, 1, 1, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
+def test_tc_conv_block(eng, case):
+    from adaptive_voice_conversion_b200 import _lib as L
+    B, Cin, Cout, K, T, shuffle, norm, use_cond, relu, res_mode = case
+    x = rnd((B, Cin, T), 1)
+    w = rnd((Cout, Cin, K), 2) / math.sqrt(Cin * K)
+    b = rnd((Cout,), 3) * 0.1
+    Tout = T
+    Cn, Tn = (Cout // 2, 2 * Tout) if shuffle else (Cout, Tout)
+    cond = (rnd((B, 2 * Cn), 4) * 0.5 + 0.7) if use_cond else None
+    res_T = {0: 0, 1: Tn, 3: Tn // 2}[res_mode]
+    res = rnd((B, Cn, res_T), 5) if res_mode else None
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    cr = cond.clone().requires_grad_(True) if cond is not None else None
+    yr = ref_block(xr, wr, b, 1, shuffle, norm, cr, relu, res, res_mode)
+    dy = rnd(tuple(yr.shape), 6)
+    yr.backward(dy)
+
+    P = {"blk.weight": w.cuda(), "blk.bias": b.cuda()}
+    G = {k: torch.zeros_like(v) for k, v in P.items()}
+    eng.packed.pop("blk", None)
+    eng.conv_names = lambda: ["blk"]
+    eng.pack_weights(P, need_dgrad=True)
+    assert "fwd_tc" in eng.packed["blk"]
+    xa = to_a4(eng, x)
+    ra = to_a4(eng, res) if res is not None else None
+    cg = cond.cuda() if cond is not None else None
+    out, rec = eng.conv(P, "blk", xa, shuffle=bool(shuffle), norm=bool(norm), cond=cg, relu=bool(relu), res=ra,
+                        res_mode=res_mode, train=True)
+    eng.check_tc_status()
+    y = from_a4(eng, out)
+    assert relerr(y, yr) < TOL, f"forward {relerr(y, yr)}"
+    if rec["c"] is not None:
+        c_ref = orc.reflect_conv1d(x, w, b)
+        assert relerr(from_a4(eng, rec["c"]), c_ref) < TOL
+    dcond = torch.zeros_like(cg) if cg is not None else None
+    dx = eng.conv_bwd(P, G, rec, to_a4(eng, dy), dcond=dcond)
+    eng.check_tc_status()
+    assert relerr(from_a4(eng, dx), xr.grad) < 2 * TOL, f"dx {relerr(from_a4(eng, dx), xr.grad)}"
+    assert relerr(G["blk.weight"], wr.grad) < 2 * TOL, f"dW {relerr(G['blk.weight'], wr.grad)}"
