@@ -15,7 +15,18 @@ import oracle.ae_oracle as orc
 
 pytestmark = pytest.mark.gpu
 
-REL = 1e-3
+REL = 1e-3   # north_star: mel reconstruction (L1) and KL loss within 1e-3 relative
+
+
+@pytest.fixture(params=["fp32", "tf32"])
+def precision(request, monkeypatch):
+    """Both arithmetic modes of the conv blocks: exact FFMA kernels and tcgen05/TF32."""
+    monkeypatch.setenv("AVC_PRECISION", request.param)
+    return request.param
+
+
+def tol(precision, fp32, tf32):
+    return fp32 if precision == "fp32" else tf32
 
 
 def relerr(a, b):
@@ -58,7 +69,7 @@ def make_model(c_in):
 
 
 @pytest.mark.parametrize("name", ["train_c80_b1.pt", "train_c80_b4.pt", "train_c512_b2.pt"])
-def test_forward_backward_vs_reference_fixture(golden_dir, name):
+def test_forward_backward_vs_reference_fixture(golden_dir, name, precision):
     """BASELINE config 1 (single segment) and friends: AE.forward + recon/KL + grads through
     loss.backward() (the autograd path) vs the reference's own outputs."""
     fx = load(golden_dir, name)
@@ -67,7 +78,7 @@ def test_forward_backward_vs_reference_fixture(golden_dir, name):
     x = fx["x"].cuda()
     mu, ls, emb, dec = model(x, eps=rec["eps"].cuda())
     for k, v in (("mu", mu), ("log_sigma", ls), ("emb", emb), ("dec", dec)):
-        assert relerr(v, rec[k]) < REL, (k, relerr(v, rec[k]))
+        assert relerr(v, rec[k]) < tol(precision, REL, 8e-3), (k, relerr(v, rec[k]))   # elementwise, of max
     loss_rec = torch.nn.L1Loss()(dec, x)
     loss_kl = 0.5 * torch.mean(torch.exp(ls) + mu ** 2 - 1 - ls)
     assert abs(float(loss_rec) - float(rec["loss_rec"])) / float(rec["loss_rec"]) < REL
@@ -77,25 +88,28 @@ def test_forward_backward_vs_reference_fixture(golden_dir, name):
     grads = {k: p.grad for k, p in model.named_parameters()}
     assert all(g is not None for g in grads.values())
     gl2 = torch.stack([grads[k].norm() for k in fx["names"]]).cpu()
-    assert torch.allclose(gl2, rec["grad_l2"], rtol=3e-2, atol=1e-5), float(((gl2 - rec["grad_l2"]).abs() / (rec["grad_l2"] + 1e-5)).max())
-    assert_grads_close(grads, rec["grad_small"], list(rec["grad_small"]))
+    # tf32: ~0.1% of ReLU masks differ from the fp32 reference -> ~3e-2 relative L2 on gradients
+    assert torch.allclose(gl2, rec["grad_l2"], rtol=tol(precision, 3e-2, 2e-1), atol=1e-5), float(((gl2 - rec["grad_l2"]).abs() / (rec["grad_l2"] + 1e-5)).max())
+    assert_grads_close(grads, rec["grad_small"], list(rec["grad_small"]), per_tensor=tol(precision, 5e-2, 3e-1), overall=tol(precision, 1e-2, 1e-1))
     total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values()))
-    assert abs(float(total) - float(rec["grad_norm"])) / float(rec["grad_norm"]) < 5e-3
+    assert abs(float(total) - float(rec["grad_norm"])) / float(rec["grad_norm"]) < tol(precision, 5e-3, 3e-2)
+    model.engine(x.device).check_tc_status()
 
 
 @pytest.mark.parametrize("name", ["infer_c80.pt", "infer_c80_t512.pt"])
-def test_inference_vs_reference_fixture(golden_dir, name):
+def test_inference_vs_reference_fixture(golden_dir, name, precision):
     """AE.inference incl. odd lengths and T_cond != T (output length 8*ceil(T/8))."""
     fx = load(golden_dir, name)
     model, _ = make_model(fx["c_in"])
     dec = model.inference(fx["x"].cuda(), fx["x_cond"].cuda())
     assert dec.shape == fx["dec"].shape
-    assert relerr(dec, fx["dec"]) < REL, relerr(dec, fx["dec"])
+    assert relerr(dec, fx["dec"]) < tol(precision, REL, 8e-3), relerr(dec, fx["dec"])
+    assert rel_l2(dec, fx["dec"]) < tol(precision, 1e-4, 3e-3)
     emb = model.get_speaker_embeddings(fx["x_cond"].cuda())
-    assert relerr(emb, fx["emb"]) < REL
+    assert relerr(emb, fx["emb"]) < tol(precision, REL, 8e-3)
 
 
-def test_forward_batch256_vs_oracle():
+def test_forward_batch256_vs_oracle(precision):
     """BASELINE config 2: batch=256 synthetic 80x128 segments, fused forward vs oracle."""
     model, cfg = make_model(80)
     g = torch.Generator().manual_seed(1)
@@ -108,7 +122,8 @@ def test_forward_batch256_vs_oracle():
         rec_r, kl_r = orc.ae_losses(x, mu_r, ls_r, dec_r)
         mu, ls, emb, dec = model(x.cuda(), eps=eps.cuda())
     for k, a, b in (("mu", mu, mu_r), ("log_sigma", ls, ls_r), ("emb", emb, emb_r), ("dec", dec, dec_r)):
-        assert relerr(a, b) < REL, (k, relerr(a, b))
+        assert relerr(a, b) < tol(precision, REL, 8e-3), (k, relerr(a, b))
+        assert rel_l2(a, b) < tol(precision, 1e-4, 3e-3), (k, rel_l2(a, b))
     rec, kl = orc.ae_losses(x, mu.cpu(), ls.cpu(), dec.cpu())
     assert abs(float(rec) - float(rec_r)) / float(rec_r) < REL
     assert abs(float(kl) - float(kl_r)) / float(kl_r) < REL
@@ -120,7 +135,7 @@ def _solver_args(tmp_path):
                                  load_model_path=str(tmp_path / "model"), summary_steps=1, save_steps=1000, tag="t", iters=0)
 
 
-def test_solver_step_vs_oracle(tmp_path):
+def test_solver_step_vs_oracle(tmp_path, precision):
     """BASELINE config 3 semantics at a small batch: Solver.ae_step (fused fwd+bwd+clip+Adam)
     vs the oracle's ae_train_step: losses, grad norm, gradients and post-step weights."""
     from adaptive_voice_conversion_b200.solver import Solver
@@ -137,13 +152,13 @@ def test_solver_step_vs_oracle(tmp_path):
         before = {k: v.detach().cpu().clone() for k, v in solver.model.state_dict().items()}
         res = orc.ae_train_step(sd, st, cfg, x, eps, 0.37)
         meta = solver.ae_step(x, 0.37, eps=eps.cuda())
-        tol = REL if it == 0 else 2e-2   # see tests/test_oracle_golden.py on Adam's sign sensitivity
-        assert abs(meta["loss_rec"] - res["loss_rec"]) / res["loss_rec"] < tol
-        assert abs(meta["loss_kl"] - res["loss_kl"]) / res["loss_kl"] < tol
-        assert abs(meta["grad_norm"] - res["grad_norm"]) / res["grad_norm"] < 10 * tol
+        t_ = REL if it == 0 else 2e-2   # see tests/test_oracle_golden.py on Adam's sign sensitivity
+        assert abs(meta["loss_rec"] - res["loss_rec"]) / res["loss_rec"] < t_
+        assert abs(meta["loss_kl"] - res["loss_kl"]) / res["loss_kl"] < t_
+        assert abs(meta["grad_norm"] - res["grad_norm"]) / res["grad_norm"] < tol(precision, 10 * t_, 5e-2)
         if it == 0:
             G = {k: v.detach().cpu().clone() for k, v in solver.trainer.G.items()}
-            assert_grads_close(G, res["grads"], list(sd))
+            assert_grads_close(G, res["grads"], list(sd), per_tensor=tol(precision, 5e-2, 3e-1), overall=tol(precision, 1e-2, 1e-1))
             # optimizer integration (flat-buffer order, clip coefficient, bias correction, amsgrad):
             # the oracle's clip+Adam applied to OUR gradients must land on OUR post-step weights
             st2 = orc.AdamState(before)
@@ -184,7 +199,7 @@ def test_graph_step_matches_eager(tmp_path):
     assert abs(outs[0][0] - outs[1][0]) / outs[0][0] < 0.05
 
 
-def test_inferencer_api(tmp_path):
+def test_inferencer_api(tmp_path, precision):
     from adaptive_voice_conversion_b200.inference import Inferencer
     cfg = orc.default_config(80)
     args = types.SimpleNamespace(attr=None, model=None, source=None, target=None, output=None, sample_rate=24000)
@@ -196,6 +211,6 @@ def test_inferencer_api(tmp_path):
     assert wav is None and mel.shape == (304, 80)
     with torch.no_grad():
         ref = orc.ae_inference(orc.init_state(cfg, 0), cfg, x.t()[None], xc.t()[None])
-    assert relerr(torch.from_numpy(mel).t()[None], ref) < REL
+    assert relerr(torch.from_numpy(mel).t()[None], ref) < tol(precision, REL, 8e-3)
     with pytest.raises(RuntimeError):
         inf.inference_from_path()

@@ -78,5 +78,35 @@ def test_tc_conv_block(eng, case):
     dcond = torch.zeros_like(cg) if cg is not None else None
     dx = eng.conv_bwd(P, G, rec, to_a4(eng, dy), dcond=dcond)
     eng.check_tc_status()
-    assert relerr(from_a4(eng, dx), xr.grad) < 2 * TOL, f"dx {relerr(from_a4(eng, dx), xr.grad)}"
-    assert relerr(G["blk.weight"], wr.grad) < 2 * TOL, f"dW {relerr(G['blk.weight'], wr.grad)}"
+    # TF32 moves pre-activations by ~1e-3, so ~0.1% of the ReLU masks differ from the fp32
+    # reference and the gradient differs by O(1) at those elements: assert in relative L2
+    # (sqrt(1e-3) ~ 3e-2 expected); the linear case below pins the dgrad kernel tightly.
+    def rl2(a, b):
+        a, b = a.double().cpu().flatten(), b.double().flatten()
+        return float((a - b).norm() / b.norm())
+    lim = 1e-1 if relu else 2 * TOL
+    assert rl2(from_a4(eng, dx), xr.grad) < lim, f"dx {rl2(from_a4(eng, dx), xr.grad)}"
+    assert rl2(G["blk.weight"], wr.grad) < lim, f"dW {rl2(G['blk.weight'], wr.grad)}"
+
+
+@pytest.mark.parametrize("B,Cin,Cout,K,T", [(5, 128, 128, 5, 128), (7, 128, 256, 5, 32), (3, 256, 128, 5, 64), (2, 128, 1104, 1, 128), (3, 128, 128, 5, 200)])
+def test_tc_dgrad_linear(eng, B, Cin, Cout, K, T):
+    """Data gradient of a plain conv (no norm / ReLU): exact transposed conv, max-norm check.
+    Cout=256 -> 2 K-slab groups in the transposed problem; Cout=1104 with dx restricted to
+    1024 channels is the in_conv -> bank gradient."""
+    x = rnd((B, Cin, T), 1).requires_grad_(True)
+    w = rnd((Cout, Cin, K), 2) / math.sqrt(Cin * K)
+    y = orc.reflect_conv1d(x, w, None)
+    dy = rnd(tuple(y.shape), 3)
+    y.backward(dy)
+    P = {"blk.weight": w.cuda(), "blk.bias": torch.zeros(Cout).cuda()}
+    G = {k: torch.zeros_like(v) for k, v in P.items()}
+    eng.packed.pop("blk", None)
+    eng.conv_names = lambda: ["blk"]
+    eng.pack_weights(P, need_dgrad=True)
+    pl, pr = K // 2, K // 2 - (1 if K % 2 == 0 else 0)
+    rec = dict(name="blk", xin=to_a4(eng, x.detach()), c=None, stats=None, cond=None, out=None, stride=1, shuffle=False, norm=False,
+               relu=False, K=K, Cin=Cin, Cout=Cout, Tout=T, pl=pl, pr=pr)
+    dx = eng.conv_bwd(P, G, rec, to_a4(eng, dy))
+    eng.check_tc_status()
+    assert relerr(from_a4(eng, dx), x.grad) < TOL, relerr(from_a4(eng, dx), x.grad)
