@@ -94,7 +94,7 @@ PROTOTYPES = {
     "avc_sqnorm": (_i, [_p, _i64, _p, _p, _p]),
     "avc_adam_step": (_i, [_p, _p, _p, _p, _p, _i64, _p, _p, _p, _p]),
     "avc_fill_zero": (_i, [_p, _i64, _p]),
-    "avc_tc_probe_gemm": (_i, [_p, _i, _p, _i, C.POINTER(C.c_uint32), _i, _i, _i, _i, _p, _p, _p]),
+    "avc_tc_probe_gemm": (_i, [_p, _i, _p, _i, C.POINTER(C.c_uint32), _i, _i, _i, _i, _i, _p, _p, _p]),
     "avc_last_error": (C.c_char_p, []),
     "avc_build_info": (C.c_char_p, []),
     "avc_launch_count": (_i64, []),

@@ -40,6 +40,23 @@ __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float(r);
 }
 
+// 4x4 transpose across the 4 lanes of a quad: in: lane r holds (a0..a3) = 4 consecutive time
+// steps of ITS channel; out: lane r holds the 4 channels of the quad at time step r.
+__device__ __forceinline__ void quad_transpose(float& a0, float& a1, float& a2, float& a3, int r) {
+  {
+    const bool odd = r & 1;
+    const float s0 = odd ? a0 : a1, s1 = odd ? a2 : a3;
+    const float g0 = __shfl_xor_sync(0xffffffffu, s0, 1), g1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+    if (odd) { a0 = g0; a2 = g1; } else { a1 = g0; a3 = g1; }
+  }
+  {
+    const bool hi = r & 2;
+    const float s0 = hi ? a0 : a2, s1 = hi ? a1 : a3;
+    const float g0 = __shfl_xor_sync(0xffffffffu, s0, 2), g1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+    if (hi) { a0 = g0; a1 = g1; } else { a2 = g0; a3 = g1; }
+  }
+}
+
 __global__ void __launch_bounds__(128, 1) conv_block_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_full[TC_MAX_STAGES], bar_ready[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_done;
@@ -162,6 +179,9 @@ __global__ void __launch_bounds__(128, 1) conv_block_tc_kernel(const TcArgs a) {
     const int Tn = shuf ? d.Tout * 2 : d.Tout;
     const int cn = shuf ? co >> 1 : co;  // normalized channel
     const int sx_ = shuf ? (co & 1) : 0;
+    const int r4 = lane & 3;             // position inside the 4-lane quad (= channel within an A4 chunk)
+    const int cq = (mtile * 128 + (tid & ~3)) >> 2;  // A4 chunk of the quad's 4 conv rows
+    const bool q_ok = (mtile * 128 + (tid & ~3)) < d.Cout;
     const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
     for (int g = 0; g < nsamp; ++g) {
       const int b = b0 + g;
@@ -197,36 +217,78 @@ __global__ void __launch_bounds__(128, 1) conv_block_tc_kernel(const TcArgs a) {
         beta = __ldg(d.cond + (size_t)b * d.cond_bstride + cn);
         gamma = __ldg(d.cond + (size_t)b * d.cond_bstride + Cn + cn);
       }
+      // raw conv (+bias) rows for backward: conv layout, always vectorizable
+      float* cbase = d.save_c ? d.save_c + (((size_t)b * (d.Cout >> 2) + cq) * d.Tout) * 4 : nullptr;
+      // non-shuffle output: the quad's 4 lanes are the 4 channels of A4 chunk cq
+      float* obase = d.out + (size_t)b * d.out_bstride + ((size_t)cq * Tn) * 4;
+      const float* rbase = d.res ? d.res + (size_t)b * d.res_bstride + ((size_t)cq * d.res_T) * 4 : nullptr;
+      const float* mbase = d.mask ? d.mask + (size_t)b * d.mask_bstride + ((size_t)cq * Tn) * 4 : nullptr;
+      // shuffle output (scalar path): channel cn, time 2t+s
       float* outp = d.out + (size_t)b * d.out_bstride + ((size_t)(cn >> 2) * Tn) * 4 + (cn & 3);
-      float* cp = d.save_c ? d.save_c + (((size_t)b * (d.Cout >> 2) + (co >> 2)) * d.Tout) * 4 + (co & 3) : nullptr;
       const float* resp = d.res ? d.res + (size_t)b * d.res_bstride + ((size_t)(cn >> 2) * d.res_T) * 4 + (cn & 3) : nullptr;
       const float* maskp = d.mask ? d.mask + (size_t)b * d.mask_bstride + ((size_t)(cn >> 2) * Tn) * 4 + (cn & 3) : nullptr;
       for (int c0 = 0; c0 < a.npad; c0 += 16) {
         float v[16];
         tc::tmem_ld16(lane_addr + (uint32_t)(g * a.npad + c0), v);
-        if (!co_ok) continue;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int t = c0 + i;
-          if (t >= d.Tout) continue;
-          float x = v[i] + bias;
-          if (cp) cp[(size_t)t * 4] = x;
-          const int tn = shuf ? 2 * t + sx_ : t;
-          if (d.norm) x = (x - mean) * rstd;
-          x = fmaf(x, gamma, beta);
-          if (d.relu) x = fmaxf(x, 0.f);
-          if (resp) {
-            float r;
-            if (d.res_mode == AVC_RES_SAME) r = __ldg(resp + (size_t)tn * 4);
-            else if (d.res_mode == AVC_RES_UP) r = __ldg(resp + (size_t)(tn >> 1) * 4);
-            else {
-              r = __ldg(resp + (size_t)(2 * tn) * 4);
-              if (2 * tn + 1 < d.res_T) r = 0.5f * (r + __ldg(resp + (size_t)(2 * tn + 1) * 4));
-            }
-            x += r;
+        for (int i4 = 0; i4 < 16; i4 += 4) {
+          float x0 = v[i4] + bias, x1 = v[i4 + 1] + bias, x2 = v[i4 + 2] + bias, x3 = v[i4 + 3] + bias;
+          const int t = c0 + i4 + r4;  // after the quad transpose this lane owns time step t for 4 channels
+          if (cbase) {
+            float y0 = x0, y1 = x1, y2 = x2, y3 = x3;
+            quad_transpose(y0, y1, y2, y3, r4);
+            if (q_ok && t < d.Tout) st4(cbase + (size_t)t * 4, make_float4(y0, y1, y2, y3));
           }
-          if (maskp && !(__ldg(maskp + (size_t)tn * 4) > 0.f)) x = 0.f;
-          outp[(size_t)tn * 4] = x;
+          if (d.norm) {
+            x0 = (x0 - mean) * rstd; x1 = (x1 - mean) * rstd; x2 = (x2 - mean) * rstd; x3 = (x3 - mean) * rstd;
+          }
+          x0 = fmaf(x0, gamma, beta); x1 = fmaf(x1, gamma, beta); x2 = fmaf(x2, gamma, beta); x3 = fmaf(x3, gamma, beta);
+          if (d.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+          if (!shuf) {
+            quad_transpose(x0, x1, x2, x3, r4);
+            if (q_ok && t < d.Tout) {
+              float4 o = make_float4(x0, x1, x2, x3);
+              if (rbase) {
+                float4 r;
+                if (d.res_mode == AVC_RES_SAME) r = ldg4(rbase + (size_t)t * 4);
+                else if (d.res_mode == AVC_RES_UP) r = ldg4(rbase + (size_t)(t >> 1) * 4);
+                else {
+                  r = ldg4(rbase + (size_t)(2 * t) * 4);
+                  if (2 * t + 1 < d.res_T) {
+                    const float4 r2 = ldg4(rbase + (size_t)(2 * t + 1) * 4);
+                    r.x = 0.5f * (r.x + r2.x); r.y = 0.5f * (r.y + r2.y); r.z = 0.5f * (r.z + r2.z); r.w = 0.5f * (r.w + r2.w);
+                  }
+                }
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+              }
+              if (mbase) {
+                const float4 m = ldg4(mbase + (size_t)t * 4);
+                o.x = m.x > 0.f ? o.x : 0.f; o.y = m.y > 0.f ? o.y : 0.f; o.z = m.z > 0.f ? o.z : 0.f; o.w = m.w > 0.f ? o.w : 0.f;
+              }
+              st4(obase + (size_t)t * 4, o);
+            }
+          } else if (co_ok) {
+            const float xs[4] = {x0, x1, x2, x3};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int tt = c0 + i4 + i;
+              if (tt >= d.Tout) continue;
+              const int tn = 2 * tt + sx_;
+              float x = xs[i];
+              if (resp) {
+                float r;
+                if (d.res_mode == AVC_RES_SAME) r = __ldg(resp + (size_t)tn * 4);
+                else if (d.res_mode == AVC_RES_UP) r = __ldg(resp + (size_t)(tn >> 1) * 4);
+                else {
+                  r = __ldg(resp + (size_t)(2 * tn) * 4);
+                  if (2 * tn + 1 < d.res_T) r = 0.5f * (r + __ldg(resp + (size_t)(2 * tn + 1) * 4));
+                }
+                x += r;
+              }
+              if (maskp && !(__ldg(maskp + (size_t)tn * 4) > 0.f)) x = 0.f;
+              outp[(size_t)tn * 4] = x;
+            }
+          }
         }
       }
     }

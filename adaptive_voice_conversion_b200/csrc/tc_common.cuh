@@ -100,13 +100,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 }
 
 // ---- descriptors
-__host__ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
+__host__ __device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 0) {
+  uint64_t d = (uint64_t)(layout & 7u) << 61;  // 0 none, 1 128B_base32B, 2 128B, 4 64B, 6 32B
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;  // descriptor version 1 (sm_100)
-  return d;                // base_offset 0, layout type 0 = no swizzle
+  return d;                // base_offset 0
 }
 // kind::tf32, fp32 accumulate, M=128; a_mn/b_mn: 1 = MN-major operand
 __host__ __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N, int a_mn, int b_mn) {

@@ -11,8 +11,8 @@ struct ProbeArgs {
   const float* a_img;
   const float* b_img;
   int a_bytes, b_bytes;
-  uint32_t a_lbo, a_sbo, b_lbo, b_sbo, a_kstep, b_kstep, a_off, b_off;
-  int nk, N;
+  uint32_t a_lbo, a_sbo, b_lbo, b_sbo, a_kstep, b_kstep, a_off, b_off, a_layout, b_layout;
+  int nk, N, reps;
   uint32_t idesc;
   float* D;
   int* status;
@@ -39,15 +39,19 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const ProbeArgs a) {
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tbase = tmem_slot;
+  long long t0 = 0;
   if (tid == 0) {
-    for (int k = 0; k < a.nk; ++k) {
-      const uint64_t ad = tc::make_sdesc(tc::smem_u32(sa) + a.a_off + k * a.a_kstep, a.a_lbo, a.a_sbo);
-      const uint64_t bd = tc::make_sdesc(tc::smem_u32(sb) + a.b_off + k * a.b_kstep, a.b_lbo, a.b_sbo);
-      tc::mma_tf32(tbase, ad, bd, a.idesc, k > 0 ? 1u : 0u);
-    }
+    t0 = clock64();
+    for (int r = 0; r < a.reps; ++r)
+      for (int k = 0; k < a.nk; ++k) {
+        const uint64_t ad = tc::make_sdesc(tc::smem_u32(sa) + a.a_off + k * a.a_kstep, a.a_lbo, a.a_sbo, a.a_layout);
+        const uint64_t bd = tc::make_sdesc(tc::smem_u32(sb) + a.b_off + k * a.b_kstep, a.b_lbo, a.b_sbo, a.b_layout);
+        tc::mma_tf32(tbase, ad, bd, a.idesc, (k > 0 || r > 0) ? 1u : 0u);
+      }
     tc::mma_commit(&bar);
   }
   const bool ok = tc::mbar_wait(&bar, 0, a.status, 1);
+  if (tid == 0) a.status[1] = (int)(clock64() - t0);  // cycles: issue of the first MMA -> all complete
   tc::tc_fence_after();
   if (ok) {
     for (int c0 = 0; c0 < a.N; c0 += 16) {
@@ -67,8 +71,8 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const ProbeArgs a) {
 
 using namespace avc;
 
-extern "C" int avc_tc_probe_gemm(const float* a_img, int a_bytes, const float* b_img, int b_bytes, const uint32_t* strides /*[8]*/,
-                                 int nk, int N, int a_mn, int b_mn, float* D, int* status, void* stream) {
+extern "C" int avc_tc_probe_gemm(const float* a_img, int a_bytes, const float* b_img, int b_bytes, const uint32_t* strides /*[10]*/,
+                                 int nk, int N, int a_mn, int b_mn, int reps, float* D, int* status, void* stream) {
   AVC_REQUIRE(a_img && b_img && strides && D && status, AVC_ERR_INVALID, "avc_tc_probe_gemm: null argument");
   AVC_REQUIRE(a_bytes % 16 == 0 && b_bytes % 16 == 0 && N % 16 == 0 && N >= 16 && N <= 256 && nk >= 1, AVC_ERR_INVALID,
               "avc_tc_probe_gemm: bad sizes");
@@ -76,7 +80,8 @@ extern "C" int avc_tc_probe_gemm(const float* a_img, int a_bytes, const float* b
   a.a_img = a_img; a.b_img = b_img; a.a_bytes = a_bytes; a.b_bytes = b_bytes;
   a.a_lbo = strides[0]; a.a_sbo = strides[1]; a.b_lbo = strides[2]; a.b_sbo = strides[3];
   a.a_kstep = strides[4]; a.b_kstep = strides[5]; a.a_off = strides[6]; a.b_off = strides[7];
-  a.nk = nk; a.N = N; a.idesc = tc::make_idesc_tf32(128, N, a_mn, b_mn); a.D = D; a.status = status;
+  a.a_layout = strides[8]; a.b_layout = strides[9];
+  a.nk = nk; a.N = N; a.reps = reps < 1 ? 1 : reps; a.idesc = tc::make_idesc_tf32(128, N, a_mn, b_mn); a.D = D; a.status = status;
   const int smem = ((a_bytes + 1023) / 1024) * 1024 + b_bytes + 1024;
   AVC_REQUIRE(smem <= 200 * 1024, AVC_ERR_INVALID, "avc_tc_probe_gemm: images too large");
   cudaError_t e = cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -155,15 +155,25 @@ def dominant_kernel_roofline(dev, batch):
     for i in range(3):
         eng.conv(P, "r", xs[i % nbuf], norm=True, relu=True, train=True)
     torch.cuda.synchronize(dev)
-    reps = 30
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-    for i in range(reps):
-        ev[i][0].record()
-        eng.conv(P, "r", xs[i % nbuf], norm=True, relu=True, train=True)
-        ev[i][1].record()
-    torch.cuda.synchronize(dev)
-    ms = sorted(a.elapsed_time(b) for a, b in ev)
-    avg_ms = sum(ms) / len(ms)
+    # the kernel is shorter than a Python launch: time a CUDA graph of `reps` back-to-back launches
+    # (rotating >L2 inputs) with events on the launching stream
+    reps = 20
+    side = torch.cuda.Stream(dev)
+    graph = torch.cuda.CUDAGraph()
+    keep = []
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for i in range(reps):
+                keep.append(eng.conv(P, "r", xs[i % nbuf], norm=True, relu=True, train=True))
+        graph.replay()
+        side.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(side)
+        for _ in range(3):
+            graph.replay()
+        e1.record(side)
+        side.synchronize()
+    avg_ms = e0.elapsed_time(e1) / (3 * reps)
     flops = 2.0 * Cc * Cc * K * T * batch
     alg_bytes = (Cc * T * batch * 4) * 3 + w.numel() * 4  # read x, write c (saved for bwd) and y, read weights
     peaks = {}

@@ -207,12 +207,13 @@ int avc_adam_step(float* p, const float* g, float* m, float* v, float* vmax, int
 int avc_fill_zero(void* ptr, int64_t bytes, void* stream);
 
 /* tcgen05 self-test (one CTA): D[128][N] = sum_k A_k * B_k^T over nk K=8 tf32 steps, the
- * operands given as raw shared-memory images; strides[8] = {a_lbo, a_sbo, b_lbo, b_sbo,
- * a_kstep, b_kstep, a_off, b_off} in bytes; a_mn/b_mn = 1 for MN-major operands.  status
- * (device int) becomes non-zero if the completion barrier timed out.  Used by the tests to
+ * operands given as raw shared-memory images; strides[10] = {a_lbo, a_sbo, b_lbo, b_sbo,
+ * a_kstep, b_kstep, a_off, b_off (bytes), a_layout, b_layout (UMMA swizzle code, 0 = none)}; a_mn/b_mn = 1 for MN-major operands; the nk steps
+ * are issued `reps` times (accumulating) for timing.  status (device int[2]): [0] non-zero if
+ * the completion barrier timed out, [1] SM cycles from first MMA issue to completion.  Used by the tests to
  * pin the UMMA descriptor conventions the conv kernels rely on. */
 int avc_tc_probe_gemm(const float* a_img, int a_bytes, const float* b_img, int b_bytes, const uint32_t* strides,
-                      int nk, int N, int a_mn, int b_mn, float* D, int* status, void* stream);
+                      int nk, int N, int a_mn, int b_mn, int reps, float* D, int* status, void* stream);
 
 const char* avc_last_error(void);
 /* "sm_100a" build tag, number of kernels launched so far by this process (for bench.py's

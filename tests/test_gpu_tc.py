@@ -18,17 +18,20 @@ def img_kmajor(mat, rows_total=None, row0=0):
     return img.contiguous()
 
 
-def run_probe(a_img, b_img, strides, nk, N, a_mn=0, b_mn=0):
+def run_probe(a_img, b_img, strides, nk, N, a_mn=0, b_mn=0, reps=1, want_cycles=False):
     from adaptive_voice_conversion_b200 import _lib as L
     lib = L.load()
     a, b = a_img.cuda().contiguous(), b_img.cuda().contiguous()
     D = torch.full((128, N), float("nan"), device="cuda")
-    status = torch.zeros(1, dtype=torch.int32, device="cuda")
-    st = (C.c_uint32 * 8)(*strides)
-    L.check(lib.avc_tc_probe_gemm(a.data_ptr(), a.numel() * 4, b.data_ptr(), b.numel() * 4, st, nk, N, a_mn, b_mn,
+    status = torch.zeros(2, dtype=torch.int32, device="cuda")
+    strides = list(strides) + [0] * (10 - len(strides))
+    st = (C.c_uint32 * 10)(*strides)
+    L.check(lib.avc_tc_probe_gemm(a.data_ptr(), a.numel() * 4, b.data_ptr(), b.numel() * 4, st, nk, N, a_mn, b_mn, reps,
                                   D.data_ptr(), status.data_ptr(), torch.cuda.current_stream().cuda_stream), "probe")
     torch.cuda.synchronize()
-    assert int(status) == 0, "tcgen05 completion barrier timed out"
+    assert int(status[0]) == 0, "tcgen05 completion barrier timed out"
+    if want_cycles:
+        return D.cpu(), int(status[1])
     return D.cpu()
 
 
