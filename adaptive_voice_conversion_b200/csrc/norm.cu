@@ -279,14 +279,15 @@ __global__ void __launch_bounds__(256) fold_add_kernel(const avc_fold_desc d) {
   }
 }
 
-// one CTA per 4-channel chunk: sum over (b, t)
+// grid (C/4 chunks, batch slices): block-reduce a slice of (b, t), one atomicAdd per channel
 __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ dc, int64_t bstride, float* __restrict__ dbias,
-                                                        int B, int C, int T) {
+                                                        int B, int C, int T, int bps) {
   const int q = blockIdx.x;
+  const int b0 = blockIdx.y * bps, b1 = min(B, b0 + bps);
   float4 s = zero4();
-  const int64_t n = (int64_t)B * T;
+  const int64_t n = (int64_t)(b1 - b0) * T;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const int b = (int)(i / T), t = (int)(i % T);
+    const int b = b0 + (int)(i / T), t = (int)(i % T);
     const float4 v = ldg4(dc + (int64_t)b * bstride + ((int64_t)q * T + t) * 4);
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
@@ -297,7 +298,8 @@ __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict_
   if (threadIdx.x == 0) {
     float4 r = zero4();
     for (int w = 0; w < 8; ++w) { r.x += part[w].x; r.y += part[w].y; r.z += part[w].z; r.w += part[w].w; }
-    dbias[q * 4 + 0] += r.x; dbias[q * 4 + 1] += r.y; dbias[q * 4 + 2] += r.z; dbias[q * 4 + 3] += r.w;
+    atomicAdd(dbias + q * 4 + 0, r.x); atomicAdd(dbias + q * 4 + 1, r.y);
+    atomicAdd(dbias + q * 4 + 2, r.z); atomicAdd(dbias + q * 4 + 3, r.w);
   }
 }
 
@@ -350,7 +352,12 @@ extern "C" int avc_fold_add_fwd(const avc_fold_desc* d, void* stream) {
 
 extern "C" int avc_bias_grad(const float* dc, int64_t bstride, float* dbias, int B, int C, int T, void* stream) {
   AVC_REQUIRE(dc && dbias && B > 0 && C > 0 && C % 4 == 0 && T > 0, AVC_ERR_INVALID, "avc_bias_grad: bad argument");
-  bias_grad_kernel<<<C / 4, 256, 0, (cudaStream_t)stream>>>(dc, bstride, dbias, B, C, T);
+  int slices = cdiv(148 * 4, C / 4);
+  if (slices > B) slices = B;
+  if (slices < 1) slices = 1;
+  const int bps = cdiv(B, slices);
+  dim3 grid(C / 4, cdiv(B, bps));
+  bias_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dc, bstride, dbias, B, C, T, bps);
   AVC_CHECK_LAUNCH("bias_grad");
   return AVC_OK;
 }

@@ -1,0 +1,234 @@
+// Conv weight gradient on the tcgen05 tensor cores (TF32 in, fp32 accumulate in TMEM):
+//   dW[co][ci][j] += sum_{b,t} dc[b][co][t] * xpad[b][ci][t + j]        (stride 1)
+// (autograd of pad_layer + nn.Conv1d w.r.t. the weight, model.py:21-32 under solver.py:90).
+//
+// GEMM view: M = co (128 per CTA), N = ci (64 per CTA), reduction K = time rows of a batch
+// slice.  Both operands are MN-major: the A4 activation layout [c/4][t][4] already keeps 4
+// channels of one time step in a 16-byte unit, so staging is a plain LDG.128 -> STS.128 of
+// units into the tensor core's MN-major TF32 layout (UMMA layout code 1, "SW128_32B"):
+//     byte(c, row) = (c/32)*LBO + row*128 + ((((c%32)/8) ^ (row%4)) * 32) + (c%8)*4
+// measured on B200 with tools/diag_mn4.py / diag_mn5.py (the XOR is keyed on the absolute
+// shared-memory row, so a descriptor start shifted by whole rows addresses shifted rows).
+// The K taps are therefore K descriptor starts (row shifts) into ONE staged input tile whose
+// reflect padding is resolved while staging; tap j accumulates into TMEM columns [j*N, (j+1)*N).
+// Each CTA owns (co tile, ci tile, batch slice); partial sums go to a scratch buffer
+// [slice][tap][ci/4][co][4] with coalesced 16-byte stores and are reduced into the canonical
+// nn.Conv1d gradient layout by wgrad_tc_reduce_kernel (deterministic, no atomics).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace avc {
+
+constexpr int WT_NT = 64;  // ci columns per CTA
+
+struct WgTcArgs {
+  avc_wgrad_desc d;
+  float* scratch;
+  int nslices, tiles_per_slice, G, RA, RX, ntpad, ncols_tmem, coutp;
+  uint32_t buf_bytes, x_off;
+  int* status;
+};
+
+__device__ __forceinline__ float rtf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float4 rtf32_4(float4 v) { return make_float4(rtf32(v.x), rtf32(v.y), rtf32(v.z), rtf32(v.w)); }
+
+// byte offset of the 16-byte unit (channel chunk q = c/4, row) inside an operand buffer
+__device__ __forceinline__ uint32_t mn_unit_off(int q, int row, uint32_t atom_bytes) {
+  return (uint32_t)(q >> 3) * atom_bytes + (uint32_t)row * 128u + (uint32_t)((((q & 7) >> 1) ^ (row & 3)) << 5) + (uint32_t)((q & 1) << 4);
+}
+
+__global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_free[2], bar_done;
+  __shared__ uint32_t tmem_slot;
+  const avc_wgrad_desc& d = a.d;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int ci0 = blockIdx.x * WT_NT, co0 = blockIdx.y * 128, sl = blockIdx.z;
+  const int K = d.K, T = d.Tout, TX = d.Tout + K - 1;  // stride 1: Tin + pl + pr = Tout + K - 1
+  const int tile0 = sl * a.tiles_per_slice;
+  const int ntiles_all = cdiv(d.B, a.G);
+  const int tile1 = min(ntiles_all, tile0 + a.tiles_per_slice);
+
+  if (tid == 0) {
+    tc::mbar_init(&bar_free[0], 1);
+    tc::mbar_init(&bar_free[1], 1);
+    tc::mbar_init(&bar_done, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, (uint32_t)a.ncols_tmem);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  const uint32_t atomA = (uint32_t)a.RA * 128u, atomX = (uint32_t)a.RX * 128u;
+  const uint32_t idesc = tc::make_idesc_tf32(128, a.ntpad, 1, 1);
+  const int nq_x = a.ntpad >> 2;  // 16-byte units per row of the x operand
+  bool ok = true;
+  bool first = true;
+
+  for (int tile = tile0; tile < tile1; ++tile) {
+    const int it = tile - tile0;
+    const int buf = it & 1;
+    if (it >= 2) ok = tc::mbar_wait(&bar_free[buf], (uint32_t)((it >> 1) - 1) & 1u, a.status, 6) && ok;
+    uint8_t* sA = smem + (size_t)buf * a.buf_bytes;
+    uint8_t* sX = sA + a.x_off;
+    const int b0 = tile * a.G;
+    const int nsamp = min(a.G, d.B - b0);
+    // ---- stage dc: [4 atoms of 32 co][G*T rows][128 B]
+    for (int q = 0; q < 32; ++q) {
+      const int co = co0 + 4 * q;
+      for (int r = tid; r < nsamp * T; r += 128) {
+        const int g = r / T, t = r - g * T;
+        float4 v = zero4();
+        if (co < d.Cout) v = ldg4(d.dc + (size_t)(b0 + g) * d.dc_bstride + ((size_t)(co >> 2) * T + t) * 4);
+        *reinterpret_cast<float4*>(sA + mn_unit_off(q, r, atomA)) = rtf32_4(v);
+      }
+    }
+    // ---- stage x with the reflect padding resolved: [ntpad/32 atoms][G*(T+K-1) rows][128 B]
+    for (int q = 0; q < nq_x; ++q) {
+      const int ci = ci0 + 4 * q;
+      for (int r = tid; r < nsamp * TX; r += 128) {
+        const int g = r / TX, u = r - g * TX;
+        float4 v = zero4();
+        if (ci < d.Cin) {
+          const int p = src_pos(u - d.pad_left, d.Tin, AVC_PAD_REFLECT, 1);
+          if (p >= 0) v = ldg4(d.x + (size_t)(b0 + g) * d.x_bstride + ((size_t)(ci >> 2) * d.Tin + p) * 4);
+        }
+        *reinterpret_cast<float4*>(sX + mn_unit_off(q, r, atomX)) = rtf32_4(v);
+      }
+    }
+    tc::fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0 && ok) {
+      tc::tc_fence_after();
+      const uint32_t aA = tc::smem_u32(sA), aX = tc::smem_u32(sX);
+      for (int g = 0; g < nsamp; ++g)
+        for (int ks = 0; ks < T / 8; ++ks) {
+          const uint64_t ad = tc::make_sdesc(aA + (uint32_t)(g * T + 8 * ks) * 128u, atomA, 512, 1);
+          for (int j = 0; j < K; ++j) {
+            const uint64_t bd = tc::make_sdesc(aX + (uint32_t)(g * TX + 8 * ks + j) * 128u, atomX, 512, 1);
+            tc::mma_tf32(tbase + (uint32_t)(j * a.ntpad), ad, bd, idesc, (first && g == 0 && ks == 0) ? 0u : 1u);
+          }
+        }
+      tc::mma_commit(&bar_free[buf]);
+    }
+    first = false;
+  }
+  if (tid == 0) tc::mma_commit(&bar_done);
+  ok = tc::mbar_wait(&bar_done, 0, a.status, 7) && ok;
+  ok = __syncthreads_and(ok) != 0;
+  tc::tc_fence_after();
+  if (ok && tile1 > tile0) {
+    // partial dW of this slice: scratch[sl][tap][ci/4][co][4]
+    const int co = co0 + tid;
+    const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
+    for (int j = 0; j < K; ++j) {
+      float* sbase = a.scratch + (((size_t)sl * K + j) * (size_t)(d.Cin >> 2)) * (size_t)a.coutp * 4;
+      for (int c0 = 0; c0 < a.ntpad; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(lane_addr + (uint32_t)(j * a.ntpad + c0), v);
+#pragma unroll
+        for (int i4 = 0; i4 < 16; i4 += 4) {
+          const int ci = ci0 + c0 + i4;
+          if (ci < d.Cin) st4(sbase + ((size_t)(ci >> 2) * a.coutp + co) * 4, make_float4(v[i4], v[i4 + 1], v[i4 + 2], v[i4 + 3]));
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tbase, (uint32_t)a.ncols_tmem);
+}
+
+// dW[co][ci][j] += sum over slices of scratch[sl][j][ci/4][co][ci%4]
+__global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __restrict__ scratch, float* __restrict__ dw, int Cout, int Cin,
+                                                              int K, int coutp, int nslices) {
+  const int64_t n = (int64_t)K * (Cin >> 2) * coutp;
+  const int64_t slice_stride = n * 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % coutp);
+    if (co >= Cout) continue;
+    const int64_t r = i / coutp;
+    const int c4 = (int)(r % (Cin >> 2)), j = (int)(r / (Cin >> 2));
+    float4 s = zero4();
+    for (int sl = 0; sl < nslices; ++sl) {
+      const float4 v = ldg4(scratch + sl * slice_stride + i * 4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    float* o = dw + ((int64_t)co * Cin + c4 * 4) * K + j;
+    o[0] += s.x; o[K] += s.y; o[2 * K] += s.z; o[3 * K] += s.w;
+  }
+}
+
+static int wgrad_tc_plan(const avc_wgrad_desc* d, WgTcArgs& a) {
+  const int T = d->Tout, K = d->K;
+  a.d = *d;
+  a.G = T >= 128 ? 1 : 128 / T;
+  a.RA = a.G * T;
+  a.RX = a.G * (T + K - 1);
+  a.ntpad = WT_NT;
+  a.coutp = cdiv(d->Cout, 128) * 128;
+  int ncols = 32;
+  while (ncols < K * a.ntpad) ncols <<= 1;
+  a.ncols_tmem = ncols;
+  a.x_off = (uint32_t)(4 * a.RA * 128 + 1023) / 1024 * 1024;
+  a.buf_bytes = (a.x_off + (uint32_t)((a.ntpad / 32) * a.RX * 128) + 1023) / 1024 * 1024;
+  const int ntiles = cdiv(d->B, a.G);
+  const int cta_per_slice = cdiv(d->Cin, WT_NT) * cdiv(d->Cout, 128);
+  int nsl = 148 / cta_per_slice;
+  if (nsl < 1) nsl = 1;
+  if (nsl > ntiles) nsl = ntiles;
+  a.tiles_per_slice = cdiv(ntiles, nsl);
+  a.nslices = cdiv(ntiles, a.tiles_per_slice);
+  return AVC_OK;
+}
+
+static bool wgrad_tc_supported(const avc_wgrad_desc* d) {
+  return d->stride == 1 && d->Tout % 8 == 0 && d->Tout <= 128 && d->K >= 1 && d->K <= 8 && d->Cin % 4 == 0 && d->Cout % 4 == 0 &&
+         d->Tin + d->K - 1 >= d->Tout;
+}
+
+}  // namespace avc
+
+using namespace avc;
+
+extern "C" int64_t avc_wgrad_tc_scratch_floats(const avc_wgrad_desc* d) {
+  if (!d || !wgrad_tc_supported(d)) return -1;
+  WgTcArgs a;
+  wgrad_tc_plan(d, a);
+  return (int64_t)a.nslices * d->K * d->Cin * a.coutp;
+}
+
+extern "C" int avc_conv_wgrad_tc(const avc_wgrad_desc* d, float* scratch, int* status, void* stream) {
+  AVC_REQUIRE(d && d->x && d->dc && d->dw && scratch && status, AVC_ERR_INVALID, "avc_conv_wgrad_tc: null argument");
+  AVC_REQUIRE(d->B > 0 && d->Cin > 0 && d->Cout > 0 && d->Tin > 0 && d->Tout > 0, AVC_ERR_INVALID, "avc_conv_wgrad_tc: bad shape");
+  AVC_REQUIRE(wgrad_tc_supported(d), AVC_ERR_UNSUPPORTED, "avc_conv_wgrad_tc: needs stride 1, Tout %% 8 == 0, Tout <= 128, K <= 8");
+  WgTcArgs a;
+  wgrad_tc_plan(d, a);
+  a.scratch = scratch;
+  a.status = status;
+  const int smem = 2 * (int)a.buf_bytes;
+  AVC_REQUIRE(smem <= 224 * 1024, AVC_ERR_UNSUPPORTED, "avc_conv_wgrad_tc: tile does not fit shared memory");
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e != cudaSuccess) {
+      set_error("avc_conv_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return AVC_ERR_CUDA;
+    }
+    attr_done = true;
+  }
+  dim3 grid(cdiv(d->Cin, WT_NT), cdiv(d->Cout, 128), a.nslices);
+  conv_wgrad_tc_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(a);
+  AVC_CHECK_LAUNCH("conv_wgrad_tc");
+  const int64_t n = (int64_t)d->K * (d->Cin / 4) * a.coutp;
+  int blocks = (int)cdiv64(n, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  wgrad_tc_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(scratch, d->dw, d->Cout, d->Cin, d->K, a.coutp, a.nslices);
+  AVC_CHECK_LAUNCH("wgrad_tc_reduce");
+  return AVC_OK;
+}

@@ -211,6 +211,16 @@ class Engine:
                        norm=norm, relu=relu, K=K, Cin=Cin, Cout=Cout, Tout=Tout, pl=pl, pr=pr)
         return out, rec
 
+    def wgrad(self, wd, name):
+        """dW += conv weight gradient; tensor cores when the shape allows, FFMA otherwise."""
+        if self.precision == "tf32":
+            n = int(self.lib.avc_wgrad_tc_scratch_floats(C.byref(wd)))
+            if n > 0:
+                scratch = self.empty(n)
+                self._ck(self.lib.avc_conv_wgrad_tc(C.byref(wd), scratch.data_ptr(), self.tc_status.data_ptr(), self.stream), f"conv_wgrad_tc[{name}]")
+                return
+        self._ck(self.lib.avc_conv_wgrad(C.byref(wd), self.stream), f"conv_wgrad[{name}]")
+
     @staticmethod
     def _fill_epilogue(d, out, shuffle, norm, relu, cond, res, res_mode, stats):
         d.out, d.out_bstride = out.ptr, out.bstride
@@ -251,7 +261,7 @@ class Engine:
         wd.B, wd.Cin, wd.Cout, wd.K, wd.stride, wd.pad_left, wd.Tin, wd.Tout = B, Cin, Cout, K, stride, rec["pl"], xin.T, Tout
         wd.x, wd.x_bstride, wd.dc, wd.dc_bstride = xin.ptr, xin.bstride, dc.ptr, dc.bstride
         wd.dw = G[name + ".weight"].data_ptr()
-        self._ck(self.lib.avc_conv_wgrad(C.byref(wd), st), f"conv_wgrad[{name}]")
+        self.wgrad(wd, name)
         if self.debug:
             self.debug(name, "dw", G[name + ".weight"])
         if not need_dx:
@@ -443,7 +453,7 @@ class Engine:
             wd.B, wd.Cin, wd.Cout, wd.K, wd.stride, wd.pad_left, wd.Tin, wd.Tout = x4.B, Cin, Cout, K, 1, pl, x4.T, Tout
             wd.x, wd.x_bstride, wd.dc, wd.dc_bstride = x4.ptr, x4.bstride, dci.ptr, dci.bstride
             wd.dw = G[name + ".weight"].data_ptr()
-            self._ck(self.lib.avc_conv_wgrad(C.byref(wd), st), f"conv_wgrad[{name}]")
+            self.wgrad(wd, name)
 
     # ------------------------------------------------------------------ reparameterisation
     def reparam_fwd(self, mu4: A4, ls4: A4, eps: Optional[torch.Tensor], want_planar=True):

@@ -124,6 +124,12 @@ typedef struct avc_wgrad_desc {
   float* dw; /* [Cout][Cin][K] */
 } avc_wgrad_desc;
 int avc_conv_wgrad(const avc_wgrad_desc* d, void* stream);
+/* The same gradient on the tcgen05 tensor cores (TF32 operands rounded to nearest, fp32
+ * accumulate; deterministic two-stage reduction through `scratch`).  Supported for stride 1,
+ * Tout % 8 == 0, Tout <= 128: avc_wgrad_tc_scratch_floats returns the scratch size in floats,
+ * or -1 when the shape must use avc_conv_wgrad.  status as in avc_conv_block_tc. */
+int64_t avc_wgrad_tc_scratch_floats(const avc_wgrad_desc* d);
+int avc_conv_wgrad_tc(const avc_wgrad_desc* d, float* scratch, int* status, void* stream);
 
 /* Adjoint of the reflect padding + residual adjoint.  dxp is the zero-padded "full"
  * transposed conv output (length Tin + pad_left + pad_right) produced by

@@ -110,3 +110,25 @@ def test_tc_dgrad_linear(eng, B, Cin, Cout, K, T):
     dx = eng.conv_bwd(P, G, rec, to_a4(eng, dy))
     eng.check_tc_status()
     assert relerr(from_a4(eng, dx), x.grad) < TOL, relerr(from_a4(eng, dx), x.grad)
+
+
+@pytest.mark.parametrize("B,Cin,Cout,K,T", [(5, 128, 128, 5, 128), (37, 128, 128, 5, 16), (9, 128, 256, 5, 32), (3, 80, 128, 8, 128),
+                                             (3, 80, 128, 1, 128), (2, 1104, 128, 1, 128), (3, 128, 80, 1, 64), (300, 128, 128, 5, 16)])
+def test_tc_wgrad(eng, B, Cin, Cout, K, T):
+    """Weight gradient on tcgen05 (MN-major operands staged from the A4 layout) vs autograd."""
+    import ctypes as C
+    from adaptive_voice_conversion_b200 import _lib as L
+    x = rnd((B, Cin, T), 1)
+    w = (rnd((Cout, Cin, K), 2) / math.sqrt(Cin * K)).requires_grad_(True)
+    y = orc.reflect_conv1d(x, w, None)
+    dc = rnd(tuple(y.shape), 3)
+    y.backward(dc)
+    xa, da = to_a4(eng, x), to_a4(eng, dc)
+    dw = torch.full((Cout, Cin, K), 0.25, device="cuda")     # accumulates (+=) into existing content
+    wd = L.WgradDesc()
+    wd.B, wd.Cin, wd.Cout, wd.K, wd.stride, wd.pad_left, wd.Tin, wd.Tout = B, Cin, Cout, K, 1, K // 2, T, T
+    wd.x, wd.x_bstride, wd.dc, wd.dc_bstride, wd.dw = xa.ptr, xa.bstride, da.ptr, da.bstride, dw.data_ptr()
+    assert int(eng.lib.avc_wgrad_tc_scratch_floats(C.byref(wd))) > 0
+    eng.wgrad(wd, "t")
+    eng.check_tc_status()
+    assert relerr(dw.cpu() - 0.25, w.grad) < TOL, relerr(dw.cpu() - 0.25, w.grad)
