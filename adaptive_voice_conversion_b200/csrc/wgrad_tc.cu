@@ -169,7 +169,8 @@ static int wgrad_tc_plan(const avc_wgrad_desc* d, WgTcArgs& a) {
   a.d = *d;
   a.G = T >= 128 ? 1 : 128 / T;
   a.RA = a.G * T;
-  a.RX = a.G * (T + K - 1);
+  a.RX = (a.G * (T + K - 1) + 3) / 4 * 4;  // atom stride must keep every atom base 512 B aligned: the
+                                            // swizzle XOR is keyed on absolute shared-memory address bits [7,9)
   a.ntpad = WT_NT;
   a.coutp = cdiv(d->Cout, 128) * 128;
   int ncols = 32;
