@@ -36,6 +36,12 @@ __device__ __forceinline__ float rtf32(float x) {
 }
 __device__ __forceinline__ float4 rtf32_4(float4 v) { return make_float4(rtf32(v.x), rtf32(v.y), rtf32(v.z), rtf32(v.w)); }
 
+// 16-byte async global->shared copy; !valid writes zeros (src-size 0, nothing is read)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
+}
+
 // byte offset of the 16-byte unit (channel chunk q = c/4, row) inside an operand buffer
 __device__ __forceinline__ uint32_t mn_unit_off(int q, int row, uint32_t atom_bytes) {
   return (uint32_t)(q >> 3) * atom_bytes + (uint32_t)row * 128u + (uint32_t)((((q & 7) >> 1) ^ (row & 3)) << 5) + (uint32_t)((q & 1) << 4);
@@ -78,29 +84,29 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
     uint8_t* sX = sA + a.x_off;
     const int b0 = tile * a.G;
     const int nsamp = min(a.G, d.B - b0);
-    // ---- stage dc: [4 atoms of 32 co][G*T rows][128 B]
+    // ---- stage dc: [4 atoms of 32 co][G*T rows][128 B]; cp.async keeps ~50 16-byte copies per
+    // thread in flight (the tensor core truncates fp32 -> tf32; a uniform ~1e-3 shrink of dW)
     for (int q = 0; q < 32; ++q) {
       const int co = co0 + 4 * q;
+      const bool cv = co < d.Cout;
       for (int r = tid; r < nsamp * T; r += 128) {
         const int g = r / T, t = r - g * T;
-        float4 v = zero4();
-        if (co < d.Cout) v = ldg4(d.dc + (size_t)(b0 + g) * d.dc_bstride + ((size_t)(co >> 2) * T + t) * 4);
-        *reinterpret_cast<float4*>(sA + mn_unit_off(q, r, atomA)) = rtf32_4(v);
+        cp_async16(sA + mn_unit_off(q, r, atomA), d.dc + (size_t)(b0 + g) * d.dc_bstride + ((size_t)((cv ? co : 0) >> 2) * T + t) * 4, cv);
       }
     }
     // ---- stage x with the reflect padding resolved: [ntpad/32 atoms][G*(T+K-1) rows][128 B]
     for (int q = 0; q < nq_x; ++q) {
       const int ci = ci0 + 4 * q;
+      const bool cv = ci < d.Cin;
       for (int r = tid; r < nsamp * TX; r += 128) {
         const int g = r / TX, u = r - g * TX;
-        float4 v = zero4();
-        if (ci < d.Cin) {
-          const int p = src_pos(u - d.pad_left, d.Tin, AVC_PAD_REFLECT, 1);
-          if (p >= 0) v = ldg4(d.x + (size_t)(b0 + g) * d.x_bstride + ((size_t)(ci >> 2) * d.Tin + p) * 4);
-        }
-        *reinterpret_cast<float4*>(sX + mn_unit_off(q, r, atomX)) = rtf32_4(v);
+        const int p = src_pos(u - d.pad_left, d.Tin, AVC_PAD_REFLECT, 1);
+        const bool v = cv && p >= 0;
+        cp_async16(sX + mn_unit_off(q, r, atomX), d.x + (size_t)(b0 + g) * d.x_bstride + ((size_t)((v ? ci : 0) >> 2) * d.Tin + (v ? p : 0)) * 4, v);
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     tc::fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0 && ok) {
