@@ -322,9 +322,66 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, float* __rest
   }
 }
 
+// All weight re-packs of a model in ONE launch: blockIdx.y walks a device-resident item table.
+__global__ void __launch_bounds__(256) pack_weights_batch_kernel(const avc_pack_item* __restrict__ items) {
+  const avc_pack_item it = items[blockIdx.y];
+  const int Cout = it.Cout, Cin = it.Cin, K = it.K;
+  const int64_t nw = (int64_t)Cout * Cin * K;
+  const int64_t n_tf = it.tc_fwd ? (int64_t)((Cout + 127) / 128) * ((Cin + TC_SLAB - 1) / TC_SLAB) * K * 2048 : 0;
+  const int64_t n_td = it.tc_dgrad ? (int64_t)((Cin + 127) / 128) * ((Cout + TC_SLAB - 1) / TC_SLAB) * K * 2048 : 0;
+  int64_t nmax = nw;
+  if (n_tf > nmax) nmax = n_tf;
+  if (n_td > nmax) nmax = n_td;
+  const float* w = it.w;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nmax; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < nw) {
+      if (it.simt_fwd) {  // P[ci][j][co] = W[co][ci][j]
+        const int co = (int)(i % Cout);
+        const int64_t r = i / Cout;
+        it.simt_fwd[i] = __ldg(w + ((int64_t)co * Cin + (int)(r / K)) * K + (int)(r % K));
+      }
+      if (it.simt_dgrad) {  // P[co][j][ci] = W[co][ci][K-1-j]
+        const int ci = (int)(i % Cin);
+        const int64_t r = i / Cin;
+        it.simt_dgrad[i] = __ldg(w + ((int64_t)(r / K) * Cin + ci) * K + (K - 1 - (int)(r % K)));
+      }
+    }
+#pragma unroll
+    for (int mode = 0; mode < 2; ++mode) {
+      float* dst = mode == 0 ? it.tc_fwd : it.tc_dgrad;
+      const int64_t n = mode == 0 ? n_tf : n_td;
+      if (!dst || i >= n) continue;
+      const int co_total = mode == 0 ? Cout : Cin, ci_total = mode == 0 ? Cin : Cout;
+      const int nslab = (ci_total + TC_SLAB - 1) / TC_SLAB;
+      int64_t r = i;
+      const int e = (int)(r % 4); r /= 4;
+      const int col = (int)(r % 128); r /= 128;
+      const int q = (int)(r % 4); r /= 4;
+      const int j = (int)(r % K); r /= K;
+      const int sl = (int)(r % nslab); r /= nslab;
+      const int co = (int)r * 128 + col, ci = sl * TC_SLAB + q * 4 + e;
+      float v = 0.f;
+      if (co < co_total && ci < ci_total)
+        v = (mode == 0) ? __ldg(w + ((int64_t)co * Cin + ci) * K + j) : __ldg(w + ((int64_t)ci * Cin + co) * K + (K - 1 - j));
+      dst[i] = round_tf32(v);
+    }
+  }
+}
+
 }  // namespace avc
 
 using namespace avc;
+
+extern "C" int avc_pack_conv_weights_batch(const avc_pack_item* items_dev, int n_items, int64_t max_elems, void* stream) {
+  AVC_REQUIRE(items_dev && n_items > 0 && max_elems > 0, AVC_ERR_INVALID, "avc_pack_conv_weights_batch: bad argument");
+  int bx = (int)cdiv64(max_elems, 256 * 4);
+  if (bx > 64) bx = 64;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, n_items);
+  pack_weights_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(items_dev);
+  AVC_CHECK_LAUNCH("pack_weights_batch");
+  return AVC_OK;
+}
 
 extern "C" int64_t avc_tc_packed_floats(int co_total, int ci_total, int K) {
   return (int64_t)((co_total + 127) / 128) * ((ci_total + TC_SLAB - 1) / TC_SLAB) * K * 4 * 128 * 4;

@@ -139,31 +139,79 @@ class Engine:
         names.append("decoder.out_conv_layer")
         return names
 
+    def _stride2_names(self):
+        names = set()
+        for enc, key in (("speaker_encoder", "SpeakerEncoder"), ("content_encoder", "ContentEncoder")):
+            c = self.cfg[key]
+            for l, s_ in enumerate(c["subsample"][: c["n_conv_blocks"]]):
+                if s_ > 1:
+                    names.add(f"{enc}.second_conv_layers.{l}")
+        return names
+
     def pack_weights(self, P: Dict[str, torch.Tensor], need_dgrad: bool, prefixes=None):
-        """nn.Conv1d weights -> kernel operand layouts (re-run whenever parameters change)."""
-        st = self.stream
-        for name in self.conv_names():
-            if prefixes is not None and not name.startswith(prefixes):
-                continue
-            w = P[name + ".weight"]
-            Cout, Cin, K = w.shape
-            slot = self.packed.setdefault(name, {})
-            if "fwd" not in slot or slot["fwd"].numel() != w.numel():
-                slot["fwd"] = self.empty(w.numel())
-            self._ck(self.lib.avc_pack_conv_weight(w.data_ptr(), slot["fwd"].data_ptr(), Cout, Cin, K, L.PACK_FWD, st), "pack_w")
-            want_dgrad = need_dgrad and ".conv_bank." not in name  # the bank's input (x) needs no gradient
-            if want_dgrad:
-                if "dgrad" not in slot or slot["dgrad"].numel() != w.numel():
-                    slot["dgrad"] = self.empty(w.numel())
-                self._ck(self.lib.avc_pack_conv_weight(w.data_ptr(), slot["dgrad"].data_ptr(), Cout, Cin, K, L.PACK_DGRAD, st), "pack_w")
-            if self.precision == "tf32":
-                for key, mode, co_t, ci_t, want in (("fwd_tc", L.PACK_FWD, Cout, Cin, True), ("dgrad_tc", L.PACK_DGRAD, Cin, Cout, want_dgrad)):
-                    if not want or ci_t % 16 != 0:
-                        continue
-                    n = int(self.lib.avc_tc_packed_floats(co_t, ci_t, K))
-                    if key not in slot or slot[key].numel() != n:
-                        slot[key] = self.empty(n)
-                    self._ck(self.lib.avc_pack_conv_weight_tc(w.data_ptr(), slot[key].data_ptr(), Cout, Cin, K, mode, st), "pack_w_tc")
+        """nn.Conv1d weights -> kernel operand layouts, ONE launch for the whole model
+        (re-run whenever parameters change).  tf32: tensor-core packs for every layer, FFMA
+        packs only for the layers that stay on the FFMA kernels (stride-2 convs); other FFMA
+        packs are produced lazily by _ensure_simt_pack (long-sequence inference)."""
+        names = [n for n in self.conv_names() if prefixes is None or n.startswith(prefixes)]
+        key = (tuple(names), bool(need_dgrad), self.precision,
+               tuple((P[n + ".weight"].data_ptr(), tuple(P[n + ".weight"].shape)) for n in names))
+        self._pack_version = getattr(self, "_pack_version", 0) + 1
+        tables = self.__dict__.setdefault("_pack_tables", {})
+        if key not in tables:
+            s2 = self._stride2_names()
+            items = (L.PackItem * len(names))()
+            max_elems = 1
+            for i, name in enumerate(names):
+                w = P[name + ".weight"]
+                Cout, Cin, K = w.shape
+                slot = self.packed.setdefault(name, {})
+                want_dgrad = need_dgrad and ".conv_bank." not in name  # the bank's input (x) needs no gradient
+                simt = self.precision == "fp32" or name in s2
+                it = items[i]
+                it.w, it.Cout, it.Cin, it.K = w.data_ptr(), Cout, Cin, K
+                max_elems = max(max_elems, w.numel())
+
+                def buf(k, n):
+                    if k not in slot or slot[k].numel() != n:
+                        slot[k] = self.empty(n)
+                        tables.clear()   # cached tables may point at the buffer just replaced
+                    return slot[k].data_ptr()
+                if simt:
+                    it.simt_fwd = buf("fwd", w.numel())
+                    if want_dgrad:
+                        it.simt_dgrad = buf("dgrad", w.numel())
+                if self.precision == "tf32":
+                    if Cin % 16 == 0:
+                        n = int(self.lib.avc_tc_packed_floats(Cout, Cin, K))
+                        it.tc_fwd = buf("fwd_tc", n)
+                        max_elems = max(max_elems, n)
+                    if want_dgrad and Cout % 16 == 0:
+                        n = int(self.lib.avc_tc_packed_floats(Cin, Cout, K))
+                        it.tc_dgrad = buf("dgrad_tc", n)
+                        max_elems = max(max_elems, n)
+            raw = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8).to(self.dev)
+            tables[key] = (raw, len(names), max_elems)
+        raw, n, max_elems = tables[key]
+        self._ck(self.lib.avc_pack_conv_weights_batch(raw.data_ptr(), n, max_elems, self.stream), "pack_weights_batch")
+        for name in names:
+            slot = self.packed[name]
+            for k in ("fwd", "dgrad"):
+                if k in slot:
+                    slot[k + "_ver"] = self._pack_version if (self.precision == "fp32" or name in self._stride2_names()) else slot.get(k + "_ver", -1)
+
+    def _ensure_simt_pack(self, P, name, key):
+        """FFMA-layout pack of one layer on demand (shapes the tensor-core path does not cover)."""
+        slot = self.packed.setdefault(name, {})
+        if slot.get(key + "_ver", -1) == getattr(self, "_pack_version", 0) and key in slot:
+            return
+        w = P[name + ".weight"]
+        Cout, Cin, K = w.shape
+        if key not in slot or slot[key].numel() != w.numel():
+            slot[key] = self.empty(w.numel())
+        mode = L.PACK_FWD if key == "fwd" else L.PACK_DGRAD
+        self._ck(self.lib.avc_pack_conv_weight(w.data_ptr(), slot[key].data_ptr(), Cout, Cin, K, mode, self.stream), "pack_w")
+        slot[key + "_ver"] = getattr(self, "_pack_version", 0)
 
     # ------------------------------------------------------------------ one conv block
     def conv(self, P, name, xin: A4, *, stride=1, shuffle=False, norm=False, cond=None, relu=False,
@@ -186,7 +234,10 @@ class Engine:
         d.B, d.Cin, d.Cout, d.K, d.stride = B, Cin, Cout, K, stride
         d.pad_left, d.pad_mode, d.in_ups, d.Tin, d.Tout = pl, L.PAD_REFLECT, 1, xin.T, Tout
         d.in_, d.in_bstride = xin.ptr, xin.bstride
-        d.w_packed, d.w_ld = self.packed[name]["fwd"].data_ptr(), Cout
+        if not use_tc:
+            self._ensure_simt_pack(P, name, "fwd")
+            d.w_packed = self.packed[name]["fwd"].data_ptr()
+        d.w_ld = Cout
         d.bias = P[name + ".bias"].data_ptr()
         d.eps = IN_EPS
         if fused:
@@ -276,7 +327,7 @@ class Engine:
         d.B, d.Cin, d.Cout, d.K, d.stride = B, Cout, Cdx, K, 1
         d.pad_left, d.pad_mode, d.in_ups, d.Tin, d.Tout = K - 1, L.PAD_ZERO, stride, Tout, Lp
         d.in_, d.in_bstride = dc.ptr, dc.bstride
-        d.w_packed, d.w_ld = self.packed[name]["dgrad"].data_ptr(), Cin
+        d.w_ld = Cin
         d.out, d.out_bstride = dxp.ptr, dxp.bstride
         d.eps = IN_EPS
         if mask is not None:
@@ -286,6 +337,8 @@ class Engine:
             d.w_tc = self.packed[name]["dgrad_tc"].data_ptr()
             self._ck(self.lib.avc_conv_block_tc(C.byref(d), self.tc_status.data_ptr(), st), f"conv_dgrad_tc[{name}]")
         else:
+            self._ensure_simt_pack(P, name, "dgrad")
+            d.w_packed = self.packed[name]["dgrad"].data_ptr()
             self._ck(self.lib.avc_conv_block_fwd(C.byref(d), st), f"conv_dgrad[{name}]")
         if direct:
             return dx

@@ -105,6 +105,17 @@ int avc_conv_block_tc(const avc_conv_desc* d, int* status, void* stream);
  * and ci_total input channels (FWD: Cout, Cin; DGRAD: Cin, Cout). */
 int avc_pack_conv_weight_tc(const float* w, float* packed, int Cout, int Cin, int K, int mode, void* stream);
 int64_t avc_tc_packed_floats(int co_total, int ci_total, int K);
+/* Every re-pack of a model in one launch: a DEVICE-resident table of items (null destinations
+ * are skipped); max_elems = the largest destination element count in the table. */
+typedef struct avc_pack_item {
+  const float* w;     /* nn.Conv1d weight [Cout][Cin][K] */
+  float* simt_fwd;    /* AVC_PACK_FWD   layout for avc_conv_block_fwd, or null */
+  float* simt_dgrad;  /* AVC_PACK_DGRAD layout for avc_conv_block_fwd, or null */
+  float* tc_fwd;      /* avc_pack_conv_weight_tc FWD layout, or null */
+  float* tc_dgrad;    /* avc_pack_conv_weight_tc DGRAD layout, or null */
+  int32_t Cout, Cin, K, reserved;
+} avc_pack_item;
+int avc_pack_conv_weights_batch(const avc_pack_item* items_dev, int n_items, int64_t max_elems, void* stream);
 /* Two-pass epilogue for long sequences: reads d->save_c, applies shuffle/norm/AdaIN/ReLU/
  * residual/mask, writes d->out and d->stats. */
 int avc_norm_apply_fwd(const avc_conv_desc* d, void* stream);
