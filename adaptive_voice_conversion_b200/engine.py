@@ -158,8 +158,14 @@ class Engine:
                tuple((P[n + ".weight"].data_ptr(), tuple(P[n + ".weight"].shape)) for n in names))
         self._pack_version = getattr(self, "_pack_version", 0) + 1
         tables = self.__dict__.setdefault("_pack_tables", {})
+        if key in tables:   # still pointing at live buffers? (tests pop / replace entries of self.packed)
+            for (nm, k), ptr in tables[key][3].items():
+                if nm not in self.packed or k not in self.packed[nm] or self.packed[nm][k].data_ptr() != ptr:
+                    del tables[key]
+                    break
         if key not in tables:
             s2 = self._stride2_names()
+            used = {}
             items = (L.PackItem * len(names))()
             max_elems = 1
             for i, name in enumerate(names):
@@ -176,6 +182,7 @@ class Engine:
                     if k not in slot or slot[k].numel() != n:
                         slot[k] = self.empty(n)
                         tables.clear()   # cached tables may point at the buffer just replaced
+                    used[(name, k)] = slot[k].data_ptr()
                     return slot[k].data_ptr()
                 if simt:
                     it.simt_fwd = buf("fwd", w.numel())
@@ -191,8 +198,8 @@ class Engine:
                         it.tc_dgrad = buf("dgrad_tc", n)
                         max_elems = max(max_elems, n)
             raw = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8).to(self.dev)
-            tables[key] = (raw, len(names), max_elems)
-        raw, n, max_elems = tables[key]
+            tables[key] = (raw, len(names), max_elems, used)
+        raw, n, max_elems, _ = tables[key]
         self._ck(self.lib.avc_pack_conv_weights_batch(raw.data_ptr(), n, max_elems, self.stream), "pack_weights_batch")
         for name in names:
             slot = self.packed[name]
