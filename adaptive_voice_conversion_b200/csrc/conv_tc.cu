@@ -183,6 +183,9 @@ __global__ void __launch_bounds__(128, 1) conv_block_tc_kernel(const TcArgs a) {
     const int cq = (mtile * 128 + (tid & ~3)) >> 2;  // A4 chunk of the quad's 4 conv rows
     const bool q_ok = (mtile * 128 + (tid & ~3)) < d.Cout;
     const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
+    // stride 2: the MMAs compute every input position; only even columns are conv outputs
+    const int sshift = d.stride == 2 ? 1 : 0, smask = sshift;
+    const int ncol = d.stride == 2 ? min(a.npad, 2 * d.Tout) : d.Tout;  // TMEM columns that matter
     for (int g = 0; g < nsamp; ++g) {
       const int b = b0 + g;
       float mean = 0.f, rstd = 1.f;
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(128, 1) conv_block_tc_kernel(const TcArgs a) {
           tc::tmem_ld16(lane_addr + (uint32_t)(g * a.npad + c0), v);
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            if (c0 + i < d.Tout) {
+            if (c0 + i < ncol && ((c0 + i) & smask) == 0) {
               const float x = v[i] + bias;
               s1 += x;
               s2 = fmaf(x, x, s2);
@@ -233,11 +236,13 @@ __global__ void __launch_bounds__(128, 1) conv_block_tc_kernel(const TcArgs a) {
 #pragma unroll
         for (int i4 = 0; i4 < 16; i4 += 4) {
           float x0 = v[i4] + bias, x1 = v[i4 + 1] + bias, x2 = v[i4 + 2] + bias, x3 = v[i4 + 3] + bias;
-          const int t = c0 + i4 + r4;  // after the quad transpose this lane owns time step t for 4 channels
+          const int tc_ = c0 + i4 + r4;  // after the quad transpose this lane owns TMEM column tc_ for 4 channels
+          const bool t_ok = tc_ < ncol && (tc_ & smask) == 0;
+          const int t = tc_ >> sshift;   // conv output time step
           if (cbase) {
             float y0 = x0, y1 = x1, y2 = x2, y3 = x3;
             quad_transpose(y0, y1, y2, y3, r4);
-            if (q_ok && t < d.Tout) st4(cbase + (size_t)t * 4, make_float4(y0, y1, y2, y3));
+            if (q_ok && t_ok) st4(cbase + (size_t)t * 4, make_float4(y0, y1, y2, y3));
           }
           if (d.norm) {
             x0 = (x0 - mean) * rstd; x1 = (x1 - mean) * rstd; x2 = (x2 - mean) * rstd; x3 = (x3 - mean) * rstd;
@@ -246,7 +251,7 @@ __global__ void __launch_bounds__(128, 1) conv_block_tc_kernel(const TcArgs a) {
           if (d.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
           if (!shuf) {
             quad_transpose(x0, x1, x2, x3, r4);
-            if (q_ok && t < d.Tout) {
+            if (q_ok && t_ok) {
               float4 o = make_float4(x0, x1, x2, x3);
               if (rbase) {
                 float4 r;
@@ -271,8 +276,9 @@ __global__ void __launch_bounds__(128, 1) conv_block_tc_kernel(const TcArgs a) {
             const float xs[4] = {x0, x1, x2, x3};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const int tt = c0 + i4 + i;
-              if (tt >= d.Tout) continue;
+              const int tcc = c0 + i4 + i;
+              if (tcc >= ncol || (tcc & smask)) continue;
+              const int tt = tcc >> sshift;
               const int tn = 2 * tt + sx_;
               float x = xs[i];
               if (resp) {
@@ -403,17 +409,19 @@ extern "C" int avc_conv_block_tc(const avc_conv_desc* d, int* status, void* stre
   int rc = validate_conv_desc(d, "avc_conv_block_tc");
   if (rc != AVC_OK) return rc;
   AVC_REQUIRE(d->in && d->w_tc && d->out && status, AVC_ERR_INVALID, "avc_conv_block_tc: null in/w_tc/out/status");
-  AVC_REQUIRE(d->stride == 1 && d->in_ups == 1, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: stride/in_ups must be 1");
+  AVC_REQUIRE((d->stride == 1 || d->stride == 2) && d->in_ups == 1, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: stride must be 1 or 2, in_ups 1");
+  AVC_REQUIRE(d->stride == 1 || !d->shuffle, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: stride 2 with pixel shuffle");
   AVC_REQUIRE(d->K >= 1 && d->K <= 8, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: K=%d not in 1..8", d->K);
   AVC_REQUIRE(d->Cin % TC_SLAB == 0, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: Cin %% 16 != 0");
-  AVC_REQUIRE(d->Tout <= 256, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: Tout > 256");
-  AVC_REQUIRE(d->Tout <= d->Tin + d->K - 1, AVC_ERR_INVALID, "avc_conv_block_tc: Tout too large for Tin");
+  const int ncols_full = d->stride == 2 ? 2 * d->Tout - 1 : d->Tout;  // stride 2: full-resolution columns 0 .. 2(Tout-1)
+  AVC_REQUIRE(ncols_full <= 256, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: more than 256 columns per sample");
+  AVC_REQUIRE(ncols_full <= d->Tin + d->K - 1, AVC_ERR_INVALID, "avc_conv_block_tc: Tout too large for Tin");
   AVC_REQUIRE(!d->res || d->res_mode != AVC_RES_NONE, AVC_ERR_INVALID, "avc_conv_block_tc: res without res_mode");
   TcArgs a;
   a.d = *d;
   if (!a.d.res) a.d.res_mode = AVC_RES_NONE;
   a.status = status;
-  a.npad = (d->Tout + 15) / 16 * 16;
+  a.npad = (ncols_full + 15) / 16 * 16;
   a.rows = a.npad + d->K - 1;
   if (a.rows < d->Tin + d->pad_left) a.rows = d->Tin + d->pad_left;  // all data rows must fit
   a.nslab = d->Cin / TC_SLAB;

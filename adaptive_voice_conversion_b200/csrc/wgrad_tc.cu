@@ -161,7 +161,15 @@ __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __res
     const int64_t r = i / coutp;
     const int c4 = (int)(r % (Cin >> 2)), j = (int)(r / (Cin >> 2));
     float4 s = zero4();
-    for (int sl = 0; sl < nslices; ++sl) {
+    int sl = 0;
+    for (; sl + 8 <= nslices; sl += 8) {  // 8 independent 16-byte loads in flight
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = ldg4(scratch + (sl + u) * slice_stride + i * 4);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+    }
+    for (; sl < nslices; ++sl) {
       const float4 v = ldg4(scratch + sl * slice_stride + i * 4);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
@@ -234,7 +242,7 @@ extern "C" int avc_conv_wgrad_tc(const avc_wgrad_desc* d, float* scratch, int* s
   AVC_CHECK_LAUNCH("conv_wgrad_tc");
   const int64_t n = (int64_t)d->K * (d->Cin / 4) * a.coutp;
   int blocks = (int)cdiv64(n, 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
   wgrad_tc_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(scratch, d->dw, d->Cout, d->Cin, d->K, a.coutp, a.nslices);
   AVC_CHECK_LAUNCH("wgrad_tc_reduce");
   return AVC_OK;

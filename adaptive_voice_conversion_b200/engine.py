@@ -233,7 +233,8 @@ class Engine:
             out = A4.empty(B, Cn, Tn, self.dev)
         assert (out.C, out.T) == (Cn, Tn)
         need_c = train and (norm or relu)
-        use_tc = (self.precision == "tf32" and stride == 1 and Cin % 16 == 0 and Tout <= 256 and "fwd_tc" in self.packed[name])
+        use_tc = (self.precision == "tf32" and Cin % 16 == 0 and Tout * stride <= 256 and not (stride == 2 and shuffle)
+                  and "fwd_tc" in self.packed[name])
         fused = use_tc or (not norm) or (Tout <= 128) or (Tout <= 256 and K in (1, 5))
         c = A4.empty(B, Cout, Tout, self.dev) if (need_c or not fused) else None
         stats = self.empty(B, Cn, 2) if norm else None

@@ -12,6 +12,10 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the CPU oracle is the slow part of the GPU suite; oneDNN on a 128-thread host is much
+    # slower oversubscribed than with a moderate thread count
+    import torch
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
 
 
 def pytest_collection_modifyitems(config, items):

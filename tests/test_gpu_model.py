@@ -116,7 +116,6 @@ def test_forward_batch256_vs_oracle(precision):
     x = torch.randn((256, 80, 128), generator=g)
     eps = torch.randn((256, 128, 16), generator=torch.Generator().manual_seed(2))
     sd = orc.init_state(cfg, seed=0)
-    torch.set_num_threads(os.cpu_count() or 1)
     with torch.no_grad():
         mu_r, ls_r, emb_r, dec_r = orc.ae_forward(sd, cfg, x, eps)
         rec_r, kl_r = orc.ae_losses(x, mu_r, ls_r, dec_r)

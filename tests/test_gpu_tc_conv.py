@@ -38,6 +38,27 @@ CASES = [
     (2, 128, 128, 5, 200, 0, 1, 0, 1, 1),     # N = 208 columns
     (2, 128, 128, 5, 256, 0, 1, 1, 1, 1),
 ]
+CASES_S2 = [(5, 128, 128, 5, 128, 1), (19, 128, 128, 5, 32, 0), (3, 128, 128, 5, 37, 1), (300, 128, 128, 5, 64, 1)]
+
+
+@pytest.mark.parametrize("B,Cin,Cout,K,T,norm", CASES_S2)
+def test_tc_conv_stride2(eng, B, Cin, Cout, K, T, norm):
+    """Stride-2 block (encoder second convs, model.py:243-249): full-resolution MMAs, even
+    columns kept, pooled residual."""
+    x = rnd((B, Cin, T), 1)
+    w = rnd((Cout, Cin, K), 2) / math.sqrt(Cin * K)
+    b = rnd((Cout,), 3) * 0.1
+    res = rnd((B, Cout, T), 5)
+    yr = ref_block(x, w, b, 2, 0, norm, None, 1, res, 2)
+    P = {"blk.weight": w.cuda(), "blk.bias": b.cuda()}
+    eng.packed.pop("blk", None)
+    eng.conv_names = lambda: ["blk"]
+    eng.pack_weights(P, need_dgrad=False)
+    out, rec = eng.conv(P, "blk", to_a4(eng, x), stride=2, norm=bool(norm), relu=True, res=to_a4(eng, res), res_mode=2, train=True)
+    eng.check_tc_status()
+    assert relerr(from_a4(eng, out), yr) < TOL, relerr(from_a4(eng, out), yr)
+    assert relerr(from_a4(eng, rec["c"]), orc.reflect_conv1d(x, w, b, 2)) < TOL
+
 
 
 @pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
