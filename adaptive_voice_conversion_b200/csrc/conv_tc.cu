@@ -137,28 +137,30 @@ __global__ void __launch_bounds__(128, 1) conv_block_tc_kernel(const TcArgs a) {
       ok = tc::mbar_wait(&bar_full[s], ph, a.status, 4);
       if (!ok) break;
       float4* sx = reinterpret_cast<float4*>(smem + (size_t)s * a.stage_bytes + a.w_bytes);
-      // data rows: round in place
+      // data rows: round in place.  One (g, t) decomposition per row, reused for the 4 chunks --
+      // the runtime integer divisions were the kernel's bottleneck when done per element.
       const int per = nsamp * d.Tin;
-      for (int idx = ptid; idx < 4 * per; idx += 64) {
-        const int q = idx / per, r = idx - q * per;
+      for (int r = ptid; r < per; r += 64) {
         const int g = r / d.Tin, t = r - g * d.Tin;
-        float4* p = sx + (size_t)q * xrows + g * a.rows + d.pad_left + t;
-        float4 v = *p;
-        v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
-        *p = v;
+        float4* p = sx + g * a.rows + d.pad_left + t;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 v = p[(size_t)q * xrows];
+          v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+          p[(size_t)q * xrows] = v;
+        }
       }
       __syncwarp();
-      // warps 1 and 3 touch disjoint (q,g,row) sets above only by index striding, so the halo
-      // rows (copies of rounded data rows) need both warps' rounding to be complete:
+      // the halo rows are copies of rounded data rows: both patch warps must be done rounding
       asm volatile("bar.sync 1, 64;" ::: "memory");
       const int halo = a.rows - d.Tin;  // rows that are not data (left pad + right pad + slack)
-      for (int idx = ptid; idx < 4 * nsamp * halo; idx += 64) {
-        const int q = idx / (nsamp * halo), r = idx - q * (nsamp * halo);
+      for (int r = ptid; r < nsamp * halo; r += 64) {
         const int g = r / halo, h = r - g * halo;
         const int u = h < d.pad_left ? h : d.Tin + h;  // row index within the sample's segment
         const int p = src_pos(u - d.pad_left, d.Tin, d.pad_mode, 1);
-        float4* base = sx + (size_t)q * xrows + g * a.rows;
-        base[u] = (p >= 0) ? base[d.pad_left + p] : zero4();
+        float4* base = sx + g * a.rows;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) base[(size_t)q * xrows + u] = (p >= 0) ? base[(size_t)q * xrows + d.pad_left + p] : zero4();
       }
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&bar_ready[s]);

@@ -85,24 +85,28 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
     const int b0 = tile * a.G;
     const int nsamp = min(a.G, d.B - b0);
     // ---- stage dc: [4 atoms of 32 co][G*T rows][128 B]; cp.async keeps ~50 16-byte copies per
-    // thread in flight (the tensor core truncates fp32 -> tf32; a uniform ~1e-3 shrink of dW)
-    for (int q = 0; q < 32; ++q) {
-      const int co = co0 + 4 * q;
-      const bool cv = co < d.Cout;
-      for (int r = tid; r < nsamp * T; r += 128) {
-        const int g = r / T, t = r - g * T;
-        cp_async16(sA + mn_unit_off(q, r, atomA), d.dc + (size_t)(b0 + g) * d.dc_bstride + ((size_t)((cv ? co : 0) >> 2) * T + t) * 4, cv);
+    // thread in flight (the tensor core truncates fp32 -> tf32; a uniform ~1e-3 shrink of dW).
+    // Row -> (sample, time) is decomposed once per row and reused for all channel chunks.
+    for (int r = tid; r < nsamp * T; r += 128) {
+      const int g = r / T, t = r - g * T;
+      const float* src = d.dc + (size_t)(b0 + g) * d.dc_bstride + (size_t)t * 4;
+#pragma unroll 8
+      for (int q = 0; q < 32; ++q) {
+        const int co = co0 + 4 * q;
+        const bool cv = co < d.Cout;
+        cp_async16(sA + mn_unit_off(q, r, atomA), src + (size_t)((cv ? co : 0) >> 2) * T * 4, cv);
       }
     }
     // ---- stage x with the reflect padding resolved: [ntpad/32 atoms][G*(T+K-1) rows][128 B]
-    for (int q = 0; q < nq_x; ++q) {
-      const int ci = ci0 + 4 * q;
-      const bool cv = ci < d.Cin;
-      for (int r = tid; r < nsamp * TX; r += 128) {
-        const int g = r / TX, u = r - g * TX;
-        const int p = src_pos(u - d.pad_left, d.Tin, AVC_PAD_REFLECT, 1);
-        const bool v = cv && p >= 0;
-        cp_async16(sX + mn_unit_off(q, r, atomX), d.x + (size_t)(b0 + g) * d.x_bstride + ((size_t)((v ? ci : 0) >> 2) * d.Tin + (v ? p : 0)) * 4, v);
+    for (int r = tid; r < nsamp * TX; r += 128) {
+      const int g = r / TX, u = r - g * TX;
+      const int p = src_pos(u - d.pad_left, d.Tin, AVC_PAD_REFLECT, 1);
+      const float* src = d.x + (size_t)(b0 + g) * d.x_bstride + (size_t)(p >= 0 ? p : 0) * 4;
+#pragma unroll 8
+      for (int q = 0; q < nq_x; ++q) {
+        const int ci = ci0 + 4 * q;
+        const bool v = ci < d.Cin && p >= 0;
+        cp_async16(sX + mn_unit_off(q, r, atomX), src + (size_t)((v ? ci : 0) >> 2) * d.Tin * 4, v);
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
