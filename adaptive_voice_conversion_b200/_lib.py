@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("AVC_LIB", os.path.join(_PKG, "libavc_b200.so"))
 PAD_REFLECT, PAD_ZERO = 0, 1
 RES_NONE, RES_SAME, RES_POOL, RES_UP = 0, 1, 2, 3
 PACK_FWD, PACK_DGRAD = 0, 1
+F_ROUND_OUT, F_IN_TF32 = 1, 2
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
 
 _fp = C.c_void_p  # device pointers travel as integers
@@ -35,7 +36,7 @@ class ConvDesc(C.Structure):
         ("save_c", _fp), ("stats", _fp),
         ("dy", _fp), ("dy_bstride", C.c_int64),
         ("dc", _fp), ("dcond", _fp), ("dcond_bstride", C.c_int64), ("dbias", _fp),
-        ("w_tc", _fp),
+        ("w_tc", _fp), ("flags", C.c_int32),
     ]
 
 
@@ -81,6 +82,7 @@ PROTOTYPES = {
     "avc_conv_block_tc": (_i, [C.POINTER(ConvDesc), _p, _p]),
     "avc_pack_conv_weight_tc": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "avc_tc_packed_floats": (_i64, [_i, _i, _i]),
+    "avc_tc_set_debug": (None, [_p]),
     "avc_pack_conv_weights_batch": (_i, [_p, _i, _i64, _p]),
     "avc_norm_apply_fwd": (_i, [C.POINTER(ConvDesc), _p]),
     "avc_norm_bwd": (_i, [C.POINTER(ConvDesc), _p]),
@@ -89,7 +91,7 @@ PROTOTYPES = {
     "avc_conv_wgrad_tc": (_i, [C.POINTER(WgradDesc), _p, _p, _p]),
     "avc_fold_add_fwd": (_i, [C.POINTER(FoldDesc), _p]),
     "avc_pack_conv_weight": (_i, [_p, _p, _i, _i, _i, _i, _p]),
-    "avc_pack_a4": (_i, [_p, _p, _i64, _i, _i, _i, _p]),
+    "avc_pack_a4": (_i, [_p, _p, _i64, _i, _i, _i, _i, _p]),
     "avc_unpack_a4": (_i, [_p, _i64, _p, _i, _i, _i, _p]),
     "avc_bias_grad": (_i, [_p, _i64, _p, _i, _i, _i, _p]),
     "avc_time_mean_fwd": (_i, [_p, _i64, _p, _i, _i, _i, _p]),

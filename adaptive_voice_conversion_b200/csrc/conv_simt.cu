@@ -41,6 +41,12 @@ struct ConvArgs {
   int seg_out, nseg, segp, tiled, ntt;
 };
 
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 struct Wf {
   float n, mean, m2;
 };
@@ -165,6 +171,9 @@ __device__ __forceinline__ void conv_epilogue(float (&acc)[8][8], const ConvArgs
         v.y = m.y > 0.f ? v.y : 0.f;
         v.z = m.z > 0.f ? v.z : 0.f;
         v.w = m.w > 0.f ? v.w : 0.f;
+      }
+      if (d.flags & AVC_F_ROUND_OUT) {
+        v = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
       }
       st4(d.out + (int64_t)b * d.out_bstride + ((int64_t)q * Tn + tn) * 4, v);
     }

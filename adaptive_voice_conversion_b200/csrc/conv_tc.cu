@@ -32,6 +32,7 @@ struct TcArgs {
   int G, npad, rows, nslab, nstage, ncols;  // samples/CTA, padded cols/sample, smem rows/sample, Cin/16, ring depth, TMEM cols
   uint32_t stage_bytes, w_bytes;
   int* status;
+  long long* dbg;  // optional: per-CTA phase timestamps (tools/diag_phases.py)
 };
 
 __device__ __forceinline__ float round_tf32(float x) {
@@ -57,7 +58,7 @@ __device__ __forceinline__ void quad_transpose(float& a0, float& a1, float& a2, 
   }
 }
 
-__global__ void __launch_bounds__(128, 1) conv_block_tc_kernel(const TcArgs a) {
+__global__ void __launch_bounds__(256, 1) conv_block_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_full[TC_MAX_STAGES], bar_ready[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_done;
   __shared__ uint32_t tmem_slot;
@@ -85,6 +86,8 @@ __global__ void __launch_bounds__(128, 1) conv_block_tc_kernel(const TcArgs a) {
   tc::tc_fence_after();
   const uint32_t tbase = tmem_slot;
   bool ok = true;
+  long long tm0 = 0, tm1 = 0, tm2 = 0, dbg_acc0 = 0, dbg_acc1 = 0;
+  if (a.dbg && tid == 64) tm0 = clock64();
 
   // ------------------------------------------------------------------ main loop (warp roles)
   if (warp == 0) {
@@ -93,7 +96,9 @@ __global__ void __launch_bounds__(128, 1) conv_block_tc_kernel(const TcArgs a) {
       for (int i = 0; i < a.nslab && ok; ++i) {
         const int s = i % a.nstage;
         const uint32_t ph = (uint32_t)(i / a.nstage) & 1u;
+        const long long w0 = a.dbg ? clock64() : 0;
         if (i >= a.nstage) ok = tc::mbar_wait(&bar_empty[s], ph ^ 1u, a.status, 2);
+        if (a.dbg) dbg_acc0 += clock64() - w0;
         if (!ok) break;
         uint8_t* sw = smem + (size_t)s * a.stage_bytes;
         uint8_t* sx = sw + a.w_bytes;
@@ -108,38 +113,55 @@ __global__ void __launch_bounds__(128, 1) conv_block_tc_kernel(const TcArgs a) {
   } else if (warp == 2) {
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc_tf32(128, a.npad, 0, 0);
+      const uint32_t d_hi = tc::sdesc_hi(128);
       for (int i = 0; i < a.nslab && ok; ++i) {
         const int s = i % a.nstage;
         const uint32_t ph = (uint32_t)(i / a.nstage) & 1u;
+        const long long w0 = a.dbg ? clock64() : 0;
         ok = tc::mbar_wait(&bar_ready[s], ph, a.status, 3);
+        const long long w1 = a.dbg ? clock64() : 0;
+        dbg_acc0 += w1 - w0;
         if (!ok) break;
         tc::tc_fence_after();
         const uint32_t sw = tc::smem_u32(smem + (size_t)s * a.stage_bytes);
         const uint32_t sx = sw + a.w_bytes;
-        for (int j = 0; j < K; ++j)
+        // descriptors differ only in the start address: one 32-bit add per MMA
+        const uint32_t a_lo0 = tc::sdesc_lo(sw, 2048), b_lo0 = tc::sdesc_lo(sx, x_chunk_bytes);
+        const uint32_t ks_b = 2u * (x_chunk_bytes >> 4);
+        for (int j = 0; j < K; ++j) {
+#pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
-            const uint64_t ad = tc::make_sdesc(sw + j * TC_WTAP_BYTES + ks * 4096, 2048, 128);
+            const uint32_t a_lo = a_lo0 + (uint32_t)j * (TC_WTAP_BYTES >> 4) + (uint32_t)ks * (4096 >> 4);
+            uint32_t b_lo = b_lo0 + (uint32_t)ks * ks_b + (uint32_t)j;
+            uint32_t dcol = tbase;
+            const uint32_t acc = (i | j | ks) ? 1u : 0u;
             for (int g = 0; g < nsamp; ++g) {
-              const uint64_t bd = tc::make_sdesc(sx + ks * 2 * x_chunk_bytes + (uint32_t)(g * a.rows + j) * 16u, x_chunk_bytes, 128);
-              tc::mma_tf32(tbase + (uint32_t)(g * a.npad), ad, bd, idesc, (i | j | ks) ? 1u : 0u);
+              tc::mma_tf32_lohi(dcol, a_lo, d_hi, b_lo, d_hi, idesc, acc);
+              b_lo += (uint32_t)a.rows;
+              dcol += (uint32_t)a.npad;
             }
           }
+        }
         tc::mma_commit(&bar_empty[s]);
+        if (a.dbg) dbg_acc1 += clock64() - w1;
       }
       if (ok) tc::mma_commit(&bar_done);
     }
-  } else {
+  } else if (warp == 1 || warp == 3) {
     // warps 1 and 3: round staged inputs to TF32 (RN) and patch the halo rows
     const int ptid = (warp == 1 ? 0 : 32) + lane;  // 0..63
     for (int i = 0; i < a.nslab && ok; ++i) {
       const int s = i % a.nstage;
       const uint32_t ph = (uint32_t)(i / a.nstage) & 1u;
+      const long long w0 = a.dbg ? clock64() : 0;
       ok = tc::mbar_wait(&bar_full[s], ph, a.status, 4);
+      const long long w1 = a.dbg ? clock64() : 0;
+      dbg_acc0 += w1 - w0;
       if (!ok) break;
       float4* sx = reinterpret_cast<float4*>(smem + (size_t)s * a.stage_bytes + a.w_bytes);
       // data rows: round in place.  One (g, t) decomposition per row, reused for the 4 chunks --
       // the runtime integer divisions were the kernel's bottleneck when done per element.
-      const int per = nsamp * d.Tin;
+      const int per = (d.flags & AVC_F_IN_TF32) ? 0 : nsamp * d.Tin;
       for (int r = ptid; r < per; r += 64) {
         const int g = r / d.Tin, t = r - g * d.Tin;
         float4* p = sx + g * a.rows + d.pad_left + t;
@@ -164,7 +186,12 @@ __global__ void __launch_bounds__(128, 1) conv_block_tc_kernel(const TcArgs a) {
       }
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&bar_ready[s]);
+      if (a.dbg) dbg_acc1 += clock64() - w1;
     }
+  }
+  if (a.dbg && (tid == 0 || tid == 32 || tid == 64)) {  // producer / patcher / MMA thread: wait, work cycles
+    long long* o = a.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 12 + 4 + (tid >> 5) * 2;
+    o[0] = dbg_acc0; o[1] = dbg_acc1;
   }
 
   // ------------------------------------------------------------------ epilogue (all warps)
@@ -172,7 +199,9 @@ __global__ void __launch_bounds__(128, 1) conv_block_tc_kernel(const TcArgs a) {
   ok = tc::mbar_wait(&bar_done, 0, a.status, 5) && ok;
   ok = __syncthreads_and(ok) != 0;  // block-uniform: the TMEM loads below are .sync.aligned
   tc::tc_fence_after();
-  const int co = mtile * 128 + tid;  // conv output row of this thread
+  if (a.dbg && tid == 64) tm1 = clock64();
+  const int etid = tid & 127, ewarp = warp & 3, egrp = warp >> 2;  // 8 epilogue warps: 2 per TMEM lane quarter
+  const int co = mtile * 128 + etid;  // conv output row of this thread
   const bool co_ok = co < d.Cout;
   if (ok) {
     const float bias = (d.bias && co_ok) ? __ldg(d.bias + co) : 0.f;
@@ -182,13 +211,13 @@ __global__ void __launch_bounds__(128, 1) conv_block_tc_kernel(const TcArgs a) {
     const int cn = shuf ? co >> 1 : co;  // normalized channel
     const int sx_ = shuf ? (co & 1) : 0;
     const int r4 = lane & 3;             // position inside the 4-lane quad (= channel within an A4 chunk)
-    const int cq = (mtile * 128 + (tid & ~3)) >> 2;  // A4 chunk of the quad's 4 conv rows
-    const bool q_ok = (mtile * 128 + (tid & ~3)) < d.Cout;
-    const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
+    const int cq = (mtile * 128 + (etid & ~3)) >> 2;  // A4 chunk of the quad's 4 conv rows
+    const bool q_ok = (mtile * 128 + (etid & ~3)) < d.Cout;
+    const uint32_t lane_addr = tbase + ((uint32_t)(ewarp * 32) << 16);
     // stride 2: the MMAs compute every input position; only even columns are conv outputs
     const int sshift = d.stride == 2 ? 1 : 0, smask = sshift;
     const int ncol = d.stride == 2 ? min(a.npad, 2 * d.Tout) : d.Tout;  // TMEM columns that matter
-    for (int g = 0; g < nsamp; ++g) {
+    for (int g = egrp; g < nsamp; g += 2) {
       const int b = b0 + g;
       float mean = 0.f, rstd = 1.f;
       if (d.norm) {
@@ -272,6 +301,7 @@ __global__ void __launch_bounds__(128, 1) conv_block_tc_kernel(const TcArgs a) {
                 const float4 m = ldg4(mbase + (size_t)t * 4);
                 o.x = m.x > 0.f ? o.x : 0.f; o.y = m.y > 0.f ? o.y : 0.f; o.z = m.z > 0.f ? o.z : 0.f; o.w = m.w > 0.f ? o.w : 0.f;
               }
+              if (d.flags & AVC_F_ROUND_OUT) o = make_float4(round_tf32(o.x), round_tf32(o.y), round_tf32(o.z), round_tf32(o.w));
               st4(obase + (size_t)t * 4, o);
             }
           } else if (co_ok) {
@@ -294,12 +324,17 @@ __global__ void __launch_bounds__(128, 1) conv_block_tc_kernel(const TcArgs a) {
                 x += r;
               }
               if (maskp && !(__ldg(maskp + (size_t)tn * 4) > 0.f)) x = 0.f;
-              outp[(size_t)tn * 4] = x;
+              outp[(size_t)tn * 4] = (d.flags & AVC_F_ROUND_OUT) ? round_tf32(x) : x;
             }
           }
         }
       }
     }
+  }
+  if (a.dbg && tid == 64) {
+    tm2 = clock64();
+    long long* o = a.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 12;
+    o[0] = tm0; o[1] = tm1; o[2] = tm2; o[3] = 0;
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -407,6 +442,9 @@ extern "C" int avc_pack_conv_weight_tc(const float* w, float* packed, int Cout, 
   return AVC_OK;
 }
 
+static long long* g_tc_dbg = nullptr;
+extern "C" void avc_tc_set_debug(void* dev_buffer) { g_tc_dbg = (long long*)dev_buffer; }
+
 extern "C" int avc_conv_block_tc(const avc_conv_desc* d, int* status, void* stream) {
   int rc = validate_conv_desc(d, "avc_conv_block_tc");
   if (rc != AVC_OK) return rc;
@@ -423,6 +461,7 @@ extern "C" int avc_conv_block_tc(const avc_conv_desc* d, int* status, void* stre
   a.d = *d;
   if (!a.d.res) a.d.res_mode = AVC_RES_NONE;
   a.status = status;
+  a.dbg = g_tc_dbg;
   a.npad = (ncols_full + 15) / 16 * 16;
   a.rows = a.npad + d->K - 1;
   if (a.rows < d->Tin + d->pad_left) a.rows = d->Tin + d->pad_left;  // all data rows must fit
@@ -456,7 +495,7 @@ extern "C" int avc_conv_block_tc(const avc_conv_desc* d, int* status, void* stre
     attr_smem = smem_max;
   }
   dim3 grid(cdiv(d->B, G), mtiles);
-  conv_block_tc_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(a);
+  conv_block_tc_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
   AVC_CHECK_LAUNCH("conv_block_tc");
   return AVC_OK;
 }

@@ -12,6 +12,12 @@ namespace avc {
 
 int validate_conv_desc(const avc_conv_desc* d, const char* who);
 
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 __device__ __forceinline__ float4 warp_sum4(float4 v) {
   v.x = warp_sum(v.x);
   v.y = warp_sum(v.y);
@@ -124,6 +130,7 @@ __global__ void __launch_bounds__(256) norm_apply_fwd_kernel(const avc_conv_desc
         ov.x = m.x > 0.f ? ov.x : 0.f; ov.y = m.y > 0.f ? ov.y : 0.f;
         ov.z = m.z > 0.f ? ov.z : 0.f; ov.w = m.w > 0.f ? ov.w : 0.f;
       }
+      if (d.flags & AVC_F_ROUND_OUT) ov = make_float4(rna_tf32(ov.x), rna_tf32(ov.y), rna_tf32(ov.z), rna_tf32(ov.w));
       st4(d.out + (int64_t)b * d.out_bstride + ((int64_t)qn * Tn + tn) * 4, ov);
     }
   }
@@ -213,8 +220,8 @@ __global__ void __launch_bounds__(256) norm_bwd_kernel(const avc_conv_desc d) {
         } else {
           dv = (d.relu && !(v[sx][c] > 0.f)) ? 0.f : g[c];
         }
-        o[sx][c] = dv;
         db[sx][c] += dv;
+        o[sx][c] = (d.flags & AVC_F_ROUND_OUT) ? rna_tf32(dv) : dv;
       }
     }
     if (!SHUF) {

@@ -41,7 +41,12 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restric
 // 32x32 tile transposes through shared memory would be the classic answer; with only 4
 // channels interleaved a direct gather is already coalesced on the wide side: each thread
 // builds one float4 (4 channel rows, same t) -- reads are 4 coalesced row segments.
-__global__ void pack_a4_kernel(const float* __restrict__ pl, float* __restrict__ a4, int64_t bstride, int B, int C, int T) {
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__global__ void pack_a4_kernel(const float* __restrict__ pl, float* __restrict__ a4, int64_t bstride, int B, int C, int T, int rnd) {
   const int Cq = C >> 2;
   const int64_t n = (int64_t)B * Cq * T;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -49,7 +54,9 @@ __global__ void pack_a4_kernel(const float* __restrict__ pl, float* __restrict__
     const int64_t bq = i / T;
     const int q = (int)(bq % Cq), b = (int)(bq / Cq);
     const float* src = pl + ((int64_t)b * C + q * 4) * T + t;
-    st4(a4 + (int64_t)b * bstride + ((int64_t)q * T + t) * 4, make_float4(__ldg(src), __ldg(src + T), __ldg(src + 2 * (int64_t)T), __ldg(src + 3 * (int64_t)T)));
+    float4 v = make_float4(__ldg(src), __ldg(src + T), __ldg(src + 2 * (int64_t)T), __ldg(src + 3 * (int64_t)T));
+    if (rnd) v = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
+    st4(a4 + (int64_t)b * bstride + ((int64_t)q * T + t) * 4, v);
   }
 }
 __global__ void unpack_a4_kernel(const float* __restrict__ a4, int64_t bstride, float* __restrict__ pl, int B, int C, int T) {
@@ -370,9 +377,9 @@ extern "C" int avc_pack_conv_weight(const float* w, float* packed, int Cout, int
   return AVC_OK;
 }
 
-extern "C" int avc_pack_a4(const float* planar, float* a4, int64_t a4_bstride, int B, int C, int T, void* stream) {
+extern "C" int avc_pack_a4(const float* planar, float* a4, int64_t a4_bstride, int B, int C, int T, int round_tf32, void* stream) {
   AVC_REQUIRE(planar && a4 && B > 0 && C > 0 && C % 4 == 0 && T > 0, AVC_ERR_INVALID, "avc_pack_a4: bad argument (C %% 4 must be 0)");
-  pack_a4_kernel<<<ew_blocks((int64_t)B * (C / 4) * T), 256, 0, (cudaStream_t)stream>>>(planar, a4, a4_bstride, B, C, T);
+  pack_a4_kernel<<<ew_blocks((int64_t)B * (C / 4) * T), 256, 0, (cudaStream_t)stream>>>(planar, a4, a4_bstride, B, C, T, round_tf32);
   AVC_CHECK_LAUNCH("pack_a4");
   return AVC_OK;
 }

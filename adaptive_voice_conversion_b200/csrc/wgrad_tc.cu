@@ -115,13 +115,18 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
     __syncthreads();
     if (tid == 0 && ok) {
       tc::tc_fence_after();
-      const uint32_t aA = tc::smem_u32(sA), aX = tc::smem_u32(sX);
+      const uint32_t a_lo0 = tc::sdesc_lo(tc::smem_u32(sA), atomA), b_lo0 = tc::sdesc_lo(tc::smem_u32(sX), atomX);
+      const uint32_t hi = tc::sdesc_hi(512, 1);
       for (int g = 0; g < nsamp; ++g)
         for (int ks = 0; ks < T / 8; ++ks) {
-          const uint64_t ad = tc::make_sdesc(aA + (uint32_t)(g * T + 8 * ks) * 128u, atomA, 512, 1);
+          const uint32_t a_lo = a_lo0 + (uint32_t)(g * T + 8 * ks) * 8u;         // rows * 128 B >> 4
+          uint32_t b_lo = b_lo0 + (uint32_t)(g * TX + 8 * ks) * 8u;
+          uint32_t dcol = tbase;
+          const uint32_t acc = (first && g == 0 && ks == 0) ? 0u : 1u;
           for (int j = 0; j < K; ++j) {
-            const uint64_t bd = tc::make_sdesc(aX + (uint32_t)(g * TX + 8 * ks + j) * 128u, atomX, 512, 1);
-            tc::mma_tf32(tbase + (uint32_t)(j * a.ntpad), ad, bd, idesc, (first && g == 0 && ks == 0) ? 0u : 1u);
+            tc::mma_tf32_lohi(dcol, a_lo, hi, b_lo, hi, idesc, acc);
+            b_lo += 8u;
+            dcol += (uint32_t)a.ntpad;
           }
         }
       tc::mma_commit(&bar_free[buf]);

@@ -25,10 +25,11 @@ IN_EPS = 1e-5
 
 class A4:
     """A [B][C/4][T][4] fp32 activation, possibly a channel sub-range of a wider buffer."""
-    __slots__ = ("t", "ptr", "B", "C", "T", "bstride")
+    __slots__ = ("t", "ptr", "B", "C", "T", "bstride", "tf32")
 
-    def __init__(self, t, ptr, B, C, T, bstride):
+    def __init__(self, t, ptr, B, C, T, bstride, tf32=False):
         self.t, self.ptr, self.B, self.C, self.T, self.bstride = t, ptr, B, C, T, bstride
+        self.tf32 = tf32   # every value is TF32-exact (written by a rounding producer)
 
     @staticmethod
     def empty(B, C, T, device):
@@ -38,7 +39,7 @@ class A4:
 
     def channels(self, c0, c1):
         assert c0 % 4 == 0 and c1 % 4 == 0
-        return A4(self.t, self.ptr + (c0 // 4) * self.T * 16, self.B, c1 - c0, self.T, self.bstride)
+        return A4(self.t, self.ptr + (c0 // 4) * self.T * 16, self.B, c1 - c0, self.T, self.bstride, self.tf32)
 
     def to_planar(self):  # test/debug helper (torch ops, not on the product path)
         v = self.t if self.t.shape[1] * 4 == self.C else None
@@ -115,7 +116,10 @@ class Engine:
     def pack_a4(self, planar: torch.Tensor, dst: A4):
         B, Cc, T = planar.shape
         assert planar.is_contiguous() and planar.dtype == torch.float32
-        self._ck(self.lib.avc_pack_a4(planar.data_ptr(), dst.ptr, dst.bstride, B, Cc, T, self.stream), "pack_a4")
+        rnd = 1 if self.precision == "tf32" else 0
+        self._ck(self.lib.avc_pack_a4(planar.data_ptr(), dst.ptr, dst.bstride, B, Cc, T, rnd, self.stream), "pack_a4")
+        if rnd and dst.bstride == dst.C * dst.T:
+            dst.tf32 = True
 
     def unpack_a4(self, src: A4, planar: Optional[torch.Tensor] = None) -> torch.Tensor:
         if planar is None:
@@ -248,6 +252,10 @@ class Engine:
         d.w_ld = Cout
         d.bias = P[name + ".bias"].data_ptr()
         d.eps = IN_EPS
+        if self.precision == "tf32":
+            d.flags = L.F_ROUND_OUT | (L.F_IN_TF32 if xin.tf32 else 0)
+            if out.bstride == out.C * out.T:
+                out.tf32 = True
         if fused:
             self._fill_epilogue(d, out, shuffle, norm, relu, cond, res, res_mode, stats)
             d.save_c = c.ptr if c is not None else None
@@ -310,6 +318,9 @@ class Engine:
                 d.dcond, d.dcond_bstride = dcond.data_ptr(), dcond.stride(0)
             d.dy, d.dy_bstride = dy.ptr, dy.bstride
             d.dc, d.dbias = dc.ptr, gb.data_ptr()
+            if self.precision == "tf32":
+                d.flags = L.F_ROUND_OUT
+                dc.tf32 = True
             self._ck(self.lib.avc_norm_bwd(C.byref(d), st), f"norm_bwd[{name}]")
             if self.debug:
                 self.debug(name, "dc", dc)
@@ -338,6 +349,8 @@ class Engine:
         d.w_ld = Cin
         d.out, d.out_bstride = dxp.ptr, dxp.bstride
         d.eps = IN_EPS
+        if self.precision == "tf32" and dc.tf32:
+            d.flags = L.F_IN_TF32
         if mask is not None:
             assert direct
             d.mask, d.mask_bstride = mask.ptr, mask.bstride

@@ -45,6 +45,11 @@ extern "C" {
 #define AVC_RES_POOL 2 /* out += avg_pool1d(res, 2, ceil_mode=True)[t]    (model.py:248,319) */
 #define AVC_RES_UP 3   /* out += nearest-upsample-x2(res)[t]              (model.py:61-63,367) */
 
+/* avc_conv_desc.flags: the tensor core truncates fp32 operands to TF32; to stay unbiased the
+ * TF32 path rounds to nearest -- once, where an activation is produced. */
+#define AVC_F_ROUND_OUT 1 /* round out (conv block / norm_apply) or dc (norm_bwd) to TF32 */
+#define AVC_F_IN_TF32 2   /* `in` is already TF32-exact: avc_conv_block_tc skips its rounding pass */
+
 #define AVC_PACK_FWD 0   /* P[ci][j][co]  = W[co][ci][j]                                   */
 #define AVC_PACK_DGRAD 1 /* P[co][j][ci]  = W[co][ci][K-1-j]  (transposed, tap-flipped)     */
 
@@ -89,6 +94,7 @@ typedef struct avc_conv_desc {
   float* dbias; /* [Cout], accumulated with atomics; or null */
   /* ---- tensor-core path (avc_conv_block_tc) ---- */
   const float* w_tc; /* weights packed by avc_pack_conv_weight_tc; or null */
+  int32_t flags;     /* AVC_F_* */
 } avc_conv_desc;
 
 /* Fused block forward.  norm=1 needs the whole Tn of a sample inside one CTA tile:
@@ -105,6 +111,9 @@ int avc_conv_block_tc(const avc_conv_desc* d, int* status, void* stream);
  * and ci_total input channels (FWD: Cout, Cin; DGRAD: Cin, Cout). */
 int avc_pack_conv_weight_tc(const float* w, float* packed, int Cout, int Cin, int K, int mode, void* stream);
 int64_t avc_tc_packed_floats(int co_total, int ci_total, int K);
+/* Diagnostics: device buffer of 4 int64 per CTA receiving clock64 at kernel start / main loop
+ * done / epilogue done for subsequent avc_conv_block_tc launches (null disables). */
+void avc_tc_set_debug(void* dev_buffer);
 /* Every re-pack of a model in one launch: a DEVICE-resident table of items (null destinations
  * are skipped); max_elems = the largest destination element count in the table. */
 typedef struct avc_pack_item {
@@ -162,7 +171,7 @@ int avc_fold_add_fwd(const avc_fold_desc* d, void* stream);
 int avc_pack_conv_weight(const float* w, float* packed, int Cout, int Cin, int K, int mode, void* stream);
 
 /* planar [B][C][T] <-> A4.  add != 0 accumulates into dst instead of overwriting. */
-int avc_pack_a4(const float* planar, float* a4, int64_t a4_bstride, int B, int C, int T, void* stream);
+int avc_pack_a4(const float* planar, float* a4, int64_t a4_bstride, int B, int C, int T, int round_tf32, void* stream);
 int avc_unpack_a4(const float* a4, int64_t a4_bstride, float* planar, int B, int C, int T, void* stream);
 
 /* sum over (b, t) of an A4 tensor -> out[C] (+=): bias gradient of a conv without epilogue. */
