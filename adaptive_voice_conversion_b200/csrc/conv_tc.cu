@@ -91,62 +91,70 @@ __global__ void __launch_bounds__(256, 1) conv_block_tc_kernel(const TcArgs a) {
 
   // ------------------------------------------------------------------ main loop (warp roles)
   if (warp == 0) {
-    if (lane == 0) {
-      const float* wsrc = d.w_tc + (size_t)mtile * a.nslab * (a.w_bytes / 4);
-      for (int i = 0; i < a.nslab && ok; ++i) {
-        const int s = i % a.nstage;
-        const uint32_t ph = (uint32_t)(i / a.nstage) & 1u;
-        const long long w0 = a.dbg ? clock64() : 0;
-        if (i >= a.nstage) ok = tc::mbar_wait(&bar_empty[s], ph ^ 1u, a.status, 2);
-        if (a.dbg) dbg_acc0 += clock64() - w0;
-        if (!ok) break;
-        uint8_t* sw = smem + (size_t)s * a.stage_bytes;
-        uint8_t* sx = sw + a.w_bytes;
+    // TMA producer: warp-converged loop, one elected lane per bulk copy (uniform operands)
+    const float* wsrc = d.w_tc + (size_t)mtile * a.nslab * (a.w_bytes / 4);
+    for (int i = 0; i < a.nslab; ++i) {
+      const int s = i % a.nstage;
+      const uint32_t ph = (uint32_t)(i / a.nstage) & 1u;
+      const long long w0 = a.dbg ? clock64() : 0;
+      if (i >= a.nstage) ok = __all_sync(0xffffffffu, tc::mbar_wait(&bar_empty[s], ph ^ 1u, a.status, 2));
+      if (a.dbg) dbg_acc0 += clock64() - w0;
+      if (!ok) break;
+      uint8_t* sw = smem + (size_t)s * a.stage_bytes;
+      uint8_t* sx = sw + a.w_bytes;
+      if (tc::elect_one()) {
         tc::mbar_arrive_expect_tx(&bar_full[s], a.w_bytes + (uint32_t)nsamp * 4u * (uint32_t)d.Tin * 16u);
         tc::bulk_g2s(sw, wsrc + (size_t)i * (a.w_bytes / 4), a.w_bytes, &bar_full[s]);
-        for (int g = 0; g < nsamp; ++g)
-          for (int q = 0; q < 4; ++q)
+      }
+      __syncwarp();
+      for (int g = 0; g < nsamp; ++g)
+        for (int q = 0; q < 4; ++q)
+          if (tc::elect_one())
             tc::bulk_g2s(sx + (size_t)q * x_chunk_bytes + ((size_t)g * a.rows + d.pad_left) * 16,
                          d.in + (size_t)(b0 + g) * d.in_bstride + ((size_t)(i * 4 + q) * d.Tin) * 4, (uint32_t)d.Tin * 16u, &bar_full[s]);
-      }
     }
   } else if (warp == 2) {
-    if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc_tf32(128, a.npad, 0, 0);
-      const uint32_t d_hi = tc::sdesc_hi(128);
-      for (int i = 0; i < a.nslab && ok; ++i) {
-        const int s = i % a.nstage;
-        const uint32_t ph = (uint32_t)(i / a.nstage) & 1u;
-        const long long w0 = a.dbg ? clock64() : 0;
-        ok = tc::mbar_wait(&bar_ready[s], ph, a.status, 3);
-        const long long w1 = a.dbg ? clock64() : 0;
-        dbg_acc0 += w1 - w0;
-        if (!ok) break;
-        tc::tc_fence_after();
-        const uint32_t sw = tc::smem_u32(smem + (size_t)s * a.stage_bytes);
-        const uint32_t sx = sw + a.w_bytes;
-        // descriptors differ only in the start address: one 32-bit add per MMA
-        const uint32_t a_lo0 = tc::sdesc_lo(sw, 2048), b_lo0 = tc::sdesc_lo(sx, x_chunk_bytes);
-        const uint32_t ks_b = 2u * (x_chunk_bytes >> 4);
-        for (int j = 0; j < K; ++j) {
+    // MMA issuer.  The WHOLE warp runs this loop converged with warp-uniform values, and one
+    // elected lane executes each tcgen05 instruction: descriptors then live in uniform registers.
+    // (Issuing from inside `if (lane == 0)` made ptxas wrap every UTCHMMA in an ELECT + 5x
+    // R2UR.BROADCAST waterfall: measured 144 cycles per MMA.)
+    const uint32_t idesc = tc::make_idesc_tf32(128, a.npad, 0, 0);
+    const uint32_t d_hi = tc::sdesc_hi(128);
+    const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
+    const uint32_t smem0 = tc::smem_u32(smem);
+    for (int i = 0; i < a.nslab; ++i) {
+      const int s = i % a.nstage;
+      const uint32_t ph = (uint32_t)(i / a.nstage) & 1u;
+      const long long w0 = a.dbg ? clock64() : 0;
+      ok = __all_sync(0xffffffffu, tc::mbar_wait(&bar_ready[s], ph, a.status, 3));
+      const long long w1 = a.dbg ? clock64() : 0;
+      dbg_acc0 += w1 - w0;
+      if (!ok) break;
+      tc::tc_fence_after();
+      const uint32_t sw = smem0 + (uint32_t)s * a.stage_bytes;
+      const uint32_t sx = sw + a.w_bytes;
+      const uint32_t a_lo0 = tc::sdesc_lo(sw, 2048), b_lo0 = tc::sdesc_lo(sx, x_chunk_bytes);
+      const uint32_t ks_b = 2u * (x_chunk_bytes >> 4);
+      for (int j = 0; j < K; ++j) {
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            const uint32_t a_lo = a_lo0 + (uint32_t)j * (TC_WTAP_BYTES >> 4) + (uint32_t)ks * (4096 >> 4);
-            uint32_t b_lo = b_lo0 + (uint32_t)ks * ks_b + (uint32_t)j;
-            uint32_t dcol = tbase;
-            const uint32_t acc = (i | j | ks) ? 1u : 0u;
-            for (int g = 0; g < nsamp; ++g) {
-              tc::mma_tf32_lohi(dcol, a_lo, d_hi, b_lo, d_hi, idesc, acc);
-              b_lo += (uint32_t)a.rows;
-              dcol += (uint32_t)a.npad;
-            }
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint32_t a_lo = a_lo0 + (uint32_t)j * (TC_WTAP_BYTES >> 4) + (uint32_t)ks * (4096 >> 4);
+          uint32_t b_lo = b_lo0 + (uint32_t)ks * ks_b + (uint32_t)j;
+          uint32_t dcol = tb;
+          const uint32_t acc = (i | j | ks) ? 1u : 0u;
+          for (int g = 0; g < nsamp; ++g) {
+            if (tc::elect_one()) tc::mma_tf32_lohi(dcol, a_lo, d_hi, b_lo, d_hi, idesc, acc);
+            b_lo += (uint32_t)a.rows;
+            dcol += (uint32_t)a.npad;
           }
         }
-        tc::mma_commit(&bar_empty[s]);
-        if (a.dbg) dbg_acc1 += clock64() - w1;
       }
-      if (ok) tc::mma_commit(&bar_done);
+      __syncwarp();
+      if (tc::elect_one()) tc::mma_commit(&bar_empty[s]);
+      if (a.dbg) dbg_acc1 += clock64() - w1;
     }
+    __syncwarp();
+    if (ok && tc::elect_one()) tc::mma_commit(&bar_done);
   } else if (warp == 1 || warp == 3) {
     // warps 1 and 3: round staged inputs to TF32 (RN) and patch the halo rows
     const int ptid = (warp == 1 ? 0 : 32) + lane;  // 0..63

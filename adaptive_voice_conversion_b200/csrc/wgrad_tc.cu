@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tbase = tmem_slot;
+  const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_slot, 0);
   const uint32_t atomA = (uint32_t)a.RA * 128u, atomX = (uint32_t)a.RX * 128u;
   const uint32_t idesc = tc::make_idesc_tf32(128, a.ntpad, 1, 1);
   const int nq_x = a.ntpad >> 2;  // 16-byte units per row of the x operand
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     tc::fence_proxy_async_smem();
     __syncthreads();
-    if (tid == 0 && ok) {
+    if (warp == 0 && ok) {  // warp-converged issue loop, one elected lane per instruction (uniform descriptors)
       tc::tc_fence_after();
       const uint32_t a_lo0 = tc::sdesc_lo(tc::smem_u32(sA), atomA), b_lo0 = tc::sdesc_lo(tc::smem_u32(sX), atomX);
       const uint32_t hi = tc::sdesc_hi(512, 1);
@@ -124,16 +124,20 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
           uint32_t dcol = tbase;
           const uint32_t acc = (first && g == 0 && ks == 0) ? 0u : 1u;
           for (int j = 0; j < K; ++j) {
-            tc::mma_tf32_lohi(dcol, a_lo, hi, b_lo, hi, idesc, acc);
+            if (tc::elect_one()) tc::mma_tf32_lohi(dcol, a_lo, hi, b_lo, hi, idesc, acc);
             b_lo += 8u;
             dcol += (uint32_t)a.ntpad;
           }
         }
-      tc::mma_commit(&bar_free[buf]);
+      __syncwarp();
+      if (tc::elect_one()) tc::mma_commit(&bar_free[buf]);
     }
     first = false;
   }
-  if (tid == 0) tc::mma_commit(&bar_done);
+  if (warp == 0) {
+    __syncwarp();
+    if (tc::elect_one()) tc::mma_commit(&bar_done);
+  }
   ok = tc::mbar_wait(&bar_done, 0, a.status, 7) && ok;
   ok = __syncthreads_and(ok) != 0;
   tc::tc_fence_after();

@@ -292,4 +292,4 @@ def test_errors_are_reported(eng):
     assert eng.lib.avc_conv_block_fwd(C.byref(d), eng.stream) == L.ERR_INVALID
     assert "non-positive" in L.last_error() or "null" in L.last_error()
     x = torch.zeros(1, 6, 8).cuda()
-    assert eng.lib.avc_pack_a4(x.data_ptr(), x.data_ptr(), 48, 1, 6, 8, eng.stream) == L.ERR_INVALID  # C % 4 != 0
+    assert eng.lib.avc_pack_a4(x.data_ptr(), x.data_ptr(), 48, 1, 6, 8, 0, eng.stream) == L.ERR_INVALID  # C % 4 != 0
