@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     tc::fence_proxy_async_smem();
-    __syncthreads();
+    ok = __syncthreads_and(ok) != 0;  // also makes `ok` block-uniform for the issue loop below
     if (warp == 0 && ok) {  // warp-converged issue loop, one elected lane per instruction (uniform descriptors)
       tc::tc_fence_after();
       const uint32_t a_lo0 = tc::sdesc_lo(tc::smem_u32(sA), atomA), b_lo0 = tc::sdesc_lo(tc::smem_u32(sX), atomX);
