@@ -36,7 +36,7 @@ class ConvDesc(C.Structure):
         ("save_c", _fp), ("stats", _fp),
         ("dy", _fp), ("dy_bstride", C.c_int64),
         ("dc", _fp), ("dcond", _fp), ("dcond_bstride", C.c_int64), ("dbias", _fp),
-        ("w_tc", _fp), ("flags", C.c_int32),
+        ("w_tc", _fp), ("flags", C.c_int32), ("out_tstride", C.c_int32), ("out_toff", C.c_int32), ("out_T", C.c_int32),
     ]
 
 
@@ -61,6 +61,7 @@ class FoldDesc(C.Structure):
 
 class PackItem(C.Structure):
     _fields_ = [("w", _fp), ("simt_fwd", _fp), ("simt_dgrad", _fp), ("tc_fwd", _fp), ("tc_dgrad", _fp),
+                ("tc_dgrad_even", _fp), ("tc_dgrad_odd", _fp),
                 ("Cout", C.c_int32), ("Cin", C.c_int32), ("K", C.c_int32), ("reserved", C.c_int32)]
 
 

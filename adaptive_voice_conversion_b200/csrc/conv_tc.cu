@@ -224,6 +224,7 @@ __global__ void __launch_bounds__(256, 1) conv_block_tc_kernel(const TcArgs a) {
     const uint32_t lane_addr = tbase + ((uint32_t)(ewarp * 32) << 16);
     // stride 2: the MMAs compute every input position; only even columns are conv outputs
     const int sshift = d.stride == 2 ? 1 : 0, smask = sshift;
+    const int ots = d.out_tstride > 0 ? d.out_tstride : 1, oto = d.out_toff;  // out time index = t*ots + oto
     const int ncol = d.stride == 2 ? min(a.npad, 2 * d.Tout) : d.Tout;  // TMEM columns that matter
     for (int g = egrp; g < nsamp; g += 2) {
       const int b = b0 + g;
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(256, 1) conv_block_tc_kernel(const TcArgs a) {
       // raw conv (+bias) rows for backward: conv layout, always vectorizable
       float* cbase = d.save_c ? d.save_c + (((size_t)b * (d.Cout >> 2) + cq) * d.Tout) * 4 : nullptr;
       // non-shuffle output: the quad's 4 lanes are the 4 channels of A4 chunk cq
-      float* obase = d.out + (size_t)b * d.out_bstride + ((size_t)cq * Tn) * 4;
+      float* obase = d.out + (size_t)b * d.out_bstride + ((size_t)cq * (d.out_T > 0 ? d.out_T : Tn)) * 4;
       const float* rbase = d.res ? d.res + (size_t)b * d.res_bstride + ((size_t)cq * d.res_T) * 4 : nullptr;
       const float* mbase = d.mask ? d.mask + (size_t)b * d.mask_bstride + ((size_t)cq * Tn) * 4 : nullptr;
       // shuffle output (scalar path): channel cn, time 2t+s
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(256, 1) conv_block_tc_kernel(const TcArgs a) {
                 o.x = m.x > 0.f ? o.x : 0.f; o.y = m.y > 0.f ? o.y : 0.f; o.z = m.z > 0.f ? o.z : 0.f; o.w = m.w > 0.f ? o.w : 0.f;
               }
               if (d.flags & AVC_F_ROUND_OUT) o = make_float4(round_tf32(o.x), round_tf32(o.y), round_tf32(o.z), round_tf32(o.w));
-              st4(obase + (size_t)t * 4, o);
+              st4(obase + (size_t)(t * ots + oto) * 4, o);
             }
           } else if (co_ok) {
             const float xs[4] = {x0, x1, x2, x3};
@@ -398,19 +399,22 @@ __global__ void __launch_bounds__(256) pack_weights_batch_kernel(const avc_pack_
       }
     }
 #pragma unroll
-    for (int mode = 0; mode < 2; ++mode) {
-      float* dst = mode == 0 ? it.tc_fwd : it.tc_dgrad;
-      const int64_t n = mode == 0 ? n_tf : n_td;
-      if (!dst || i >= n) continue;
+    for (int mode = 0; mode < 4; ++mode) {  // 0 fwd, 1 dgrad, 2 dgrad even taps, 3 dgrad odd taps
+      float* dst = mode == 0 ? it.tc_fwd : mode == 1 ? it.tc_dgrad : mode == 2 ? it.tc_dgrad_even : it.tc_dgrad_odd;
+      if (!dst) continue;
       const int co_total = mode == 0 ? Cout : Cin, ci_total = mode == 0 ? Cin : Cout;
       const int nslab = (ci_total + TC_SLAB - 1) / TC_SLAB;
+      const int Ks = mode < 2 ? K : mode == 2 ? (K + 1) / 2 : K / 2;  // taps in this pack
+      const int64_t n = (int64_t)((co_total + 127) / 128) * nslab * Ks * 2048;
+      if (i >= n) continue;
       int64_t r = i;
       const int e = (int)(r % 4); r /= 4;
       const int col = (int)(r % 128); r /= 128;
       const int q = (int)(r % 4); r /= 4;
-      const int j = (int)(r % K); r /= K;
+      const int jj = (int)(r % Ks); r /= Ks;
       const int sl = (int)(r % nslab); r /= nslab;
       const int co = (int)r * 128 + col, ci = sl * TC_SLAB + q * 4 + e;
+      const int j = mode < 2 ? jj : mode == 2 ? 2 * jj : 2 * jj + 1;  // tap of the full (flipped) dgrad conv
       float v = 0.f;
       if (co < co_total && ci < ci_total)
         v = (mode == 0) ? __ldg(w + ((int64_t)co * Cin + ci) * K + j) : __ldg(w + ((int64_t)ci * Cin + co) * K + (K - 1 - j));
@@ -459,11 +463,12 @@ extern "C" int avc_conv_block_tc(const avc_conv_desc* d, int* status, void* stre
   AVC_REQUIRE(d->in && d->w_tc && d->out && status, AVC_ERR_INVALID, "avc_conv_block_tc: null in/w_tc/out/status");
   AVC_REQUIRE((d->stride == 1 || d->stride == 2) && d->in_ups == 1, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: stride must be 1 or 2, in_ups 1");
   AVC_REQUIRE(d->stride == 1 || !d->shuffle, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: stride 2 with pixel shuffle");
+  AVC_REQUIRE(d->out_tstride <= 1 || (!d->shuffle && !d->res && !d->mask && !d->norm), AVC_ERR_UNSUPPORTED,
+              "avc_conv_block_tc: out_tstride only for plain (data-gradient) convs");
   AVC_REQUIRE(d->K >= 1 && d->K <= 8, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: K=%d not in 1..8", d->K);
   AVC_REQUIRE(d->Cin % TC_SLAB == 0, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: Cin %% 16 != 0");
   const int ncols_full = d->stride == 2 ? 2 * d->Tout - 1 : d->Tout;  // stride 2: full-resolution columns 0 .. 2(Tout-1)
   AVC_REQUIRE(ncols_full <= 256, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: more than 256 columns per sample");
-  AVC_REQUIRE(ncols_full <= d->Tin + d->K - 1, AVC_ERR_INVALID, "avc_conv_block_tc: Tout too large for Tin");
   AVC_REQUIRE(!d->res || d->res_mode != AVC_RES_NONE, AVC_ERR_INVALID, "avc_conv_block_tc: res without res_mode");
   TcArgs a;
   a.d = *d;

@@ -24,7 +24,7 @@ constexpr int WT_NT = 64;  // ci columns per CTA
 struct WgTcArgs {
   avc_wgrad_desc d;
   float* scratch;
-  int nslices, tiles_per_slice, G, RA, RX, ntpad, ncols_tmem, coutp;
+  int nslices, tiles_per_slice, G, RA, RX, ntpad, ncols_tmem, coutp, TX, H;  // H: rows of one parity block (stride 2)
   uint32_t buf_bytes, x_off;
   int* status;
 };
@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
   const avc_wgrad_desc& d = a.d;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int ci0 = blockIdx.x * WT_NT, co0 = blockIdx.y * 128, sl = blockIdx.z;
-  const int K = d.K, T = d.Tout, TX = d.Tout + K - 1;  // stride 1: Tin + pl + pr = Tout + K - 1
+  const int K = d.K, T = d.Tout, TX = a.TX;  // padded input positions per sample
+  const int S = d.stride, H = a.H;
   const int tile0 = sl * a.tiles_per_slice;
   const int ntiles_all = cdiv(d.B, a.G);
   const int tile1 = min(ntiles_all, tile0 + a.tiles_per_slice);
@@ -98,8 +99,11 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
       }
     }
     // ---- stage x with the reflect padding resolved: [ntpad/32 atoms][G*(T+K-1) rows][128 B]
-    for (int r = tid; r < nsamp * TX; r += 128) {
-      const int g = r / TX, u = r - g * TX;
+    for (int r0 = tid; r0 < nsamp * TX; r0 += 128) {
+      const int g = r0 / TX, u = r0 - g * TX;
+      // stride 2: even and odd padded positions go to separate row blocks, so tap j addresses
+      // rows (j&1)*H + t + (j>>1) -- contiguous in t
+      const int r = S == 1 ? r0 : g * 2 * H + (u & 1) * H + (u >> 1);
       const int p = src_pos(u - d.pad_left, d.Tin, AVC_PAD_REFLECT, 1);
       const float* src = d.x + (size_t)(b0 + g) * d.x_bstride + (size_t)(p >= 0 ? p : 0) * 4;
 #pragma unroll 8
@@ -120,12 +124,12 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
       for (int g = 0; g < nsamp; ++g)
         for (int ks = 0; ks < T / 8; ++ks) {
           const uint32_t a_lo = a_lo0 + (uint32_t)(g * T + 8 * ks) * 8u;         // rows * 128 B >> 4
-          uint32_t b_lo = b_lo0 + (uint32_t)(g * TX + 8 * ks) * 8u;
+          const uint32_t b_base = b_lo0 + (uint32_t)((S == 1 ? g * TX : g * 2 * H) + 8 * ks) * 8u;
           uint32_t dcol = tbase;
           const uint32_t acc = (first && g == 0 && ks == 0) ? 0u : 1u;
           for (int j = 0; j < K; ++j) {
+            const uint32_t b_lo = b_base + (uint32_t)(S == 1 ? j : (j & 1) * H + (j >> 1)) * 8u;
             if (tc::elect_one()) tc::mma_tf32_lohi(dcol, a_lo, hi, b_lo, hi, idesc, acc);
-            b_lo += 8u;
             dcol += (uint32_t)a.ntpad;
           }
         }
@@ -164,30 +168,31 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
 }
 
 // dW[co][ci][j] += sum over slices of scratch[sl][j][ci/4][co][ci%4]
+// block (32, 8): x = output float4 (coalesced 512 B per warp), y = slice group
 __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __restrict__ scratch, float* __restrict__ dw, int Cout, int Cin,
                                                               int K, int coutp, int nslices) {
+  __shared__ float4 part[8][32];
   const int64_t n = (int64_t)K * (Cin >> 2) * coutp;
   const int64_t slice_stride = n * 4;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int co = (int)(i % coutp);
-    if (co >= Cout) continue;
-    const int64_t r = i / coutp;
-    const int c4 = (int)(r % (Cin >> 2)), j = (int)(r / (Cin >> 2));
-    float4 s = zero4();
-    int sl = 0;
-    for (; sl + 8 <= nslices; sl += 8) {  // 8 independent 16-byte loads in flight
-      float4 v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = ldg4(scratch + (sl + u) * slice_stride + i * 4);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
-    }
-    for (; sl < nslices; ++sl) {
+  const int64_t i = (int64_t)blockIdx.x * 32 + threadIdx.x;
+  float4 s = zero4();
+  if (i < n)
+    for (int sl = threadIdx.y; sl < nslices; sl += 8) {
       const float4 v = ldg4(scratch + sl * slice_stride + i * 4);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
-    float* o = dw + ((int64_t)co * Cin + c4 * 4) * K + j;
-    o[0] += s.x; o[K] += s.y; o[2 * K] += s.z; o[3 * K] += s.w;
+  part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < n) {
+#pragma unroll
+    for (int y = 1; y < 8; ++y) { const float4 v = part[y][threadIdx.x]; s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+    const int co = (int)(i % coutp);
+    if (co < Cout) {
+      const int64_t r = i / coutp;
+      const int c4 = (int)(r % (Cin >> 2)), j = (int)(r / (Cin >> 2));
+      float* o = dw + ((int64_t)co * Cin + c4 * 4) * K + j;
+      o[0] += s.x; o[K] += s.y; o[2 * K] += s.z; o[3 * K] += s.w;
+    }
   }
 }
 
@@ -195,9 +200,14 @@ static int wgrad_tc_plan(const avc_wgrad_desc* d, WgTcArgs& a) {
   const int T = d->Tout, K = d->K;
   a.d = *d;
   a.G = T >= 128 ? 1 : 128 / T;
+  if (d->stride == 2) a.G = T >= 64 ? 1 : 64 / T;  // the parity-split input tile is twice as tall
   a.RA = a.G * T;
-  a.RX = (a.G * (T + K - 1) + 3) / 4 * 4;  // atom stride must keep every atom base 512 B aligned: the
-                                            // swizzle XOR is keyed on absolute shared-memory address bits [7,9)
+  // padded input positions one sample contributes: stride 1: T+K-1; stride 2: 2(T-1)+K
+  a.TX = d->stride == 1 ? T + K - 1 : 2 * (T - 1) + K;
+  a.H = ((a.TX + 1) / 2 + 3) / 4 * 4;
+  // atom stride must keep every atom base 512 B aligned: the swizzle XOR is keyed on absolute
+  // shared-memory address bits [7,9)
+  a.RX = d->stride == 1 ? (a.G * a.TX + 3) / 4 * 4 : a.G * 2 * a.H;
   a.ntpad = WT_NT;
   a.coutp = cdiv(d->Cout, 128) * 128;
   int ncols = 32;
@@ -216,8 +226,8 @@ static int wgrad_tc_plan(const avc_wgrad_desc* d, WgTcArgs& a) {
 }
 
 static bool wgrad_tc_supported(const avc_wgrad_desc* d) {
-  return d->stride == 1 && d->Tout % 8 == 0 && d->Tout <= 128 && d->K >= 1 && d->K <= 8 && d->Cin % 4 == 0 && d->Cout % 4 == 0 &&
-         d->Tin + d->K - 1 >= d->Tout;
+  return (d->stride == 1 || d->stride == 2) && d->Tout % 8 == 0 && d->Tout <= 128 && d->K >= 1 && d->K <= 8 && d->Cin % 4 == 0 &&
+         d->Cout % 4 == 0 && d->Tin + d->K - 1 >= (d->Tout - 1) * d->stride + 1 && (d->stride == 1 || d->Tout <= 64);
 }
 
 }  // namespace avc
@@ -234,7 +244,7 @@ extern "C" int64_t avc_wgrad_tc_scratch_floats(const avc_wgrad_desc* d) {
 extern "C" int avc_conv_wgrad_tc(const avc_wgrad_desc* d, float* scratch, int* status, void* stream) {
   AVC_REQUIRE(d && d->x && d->dc && d->dw && scratch && status, AVC_ERR_INVALID, "avc_conv_wgrad_tc: null argument");
   AVC_REQUIRE(d->B > 0 && d->Cin > 0 && d->Cout > 0 && d->Tin > 0 && d->Tout > 0, AVC_ERR_INVALID, "avc_conv_wgrad_tc: bad shape");
-  AVC_REQUIRE(wgrad_tc_supported(d), AVC_ERR_UNSUPPORTED, "avc_conv_wgrad_tc: needs stride 1, Tout %% 8 == 0, Tout <= 128, K <= 8");
+  AVC_REQUIRE(wgrad_tc_supported(d), AVC_ERR_UNSUPPORTED, "avc_conv_wgrad_tc: needs stride 1 (Tout <= 128) or 2 (Tout <= 64), Tout %% 8 == 0, K <= 8");
   WgTcArgs a;
   wgrad_tc_plan(d, a);
   a.scratch = scratch;
@@ -254,9 +264,7 @@ extern "C" int avc_conv_wgrad_tc(const avc_wgrad_desc* d, float* scratch, int* s
   conv_wgrad_tc_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(a);
   AVC_CHECK_LAUNCH("conv_wgrad_tc");
   const int64_t n = (int64_t)d->K * (d->Cin / 4) * a.coutp;
-  int blocks = (int)cdiv64(n, 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  wgrad_tc_reduce_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(scratch, d->dw, d->Cout, d->Cin, d->K, a.coutp, a.nslices);
+  wgrad_tc_reduce_kernel<<<(int)cdiv64(n, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(scratch, d->dw, d->Cout, d->Cin, d->K, a.coutp, a.nslices);
   AVC_CHECK_LAUNCH("wgrad_tc_reduce");
   return AVC_OK;
 }

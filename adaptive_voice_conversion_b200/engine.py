@@ -201,6 +201,9 @@ class Engine:
                         n = int(self.lib.avc_tc_packed_floats(Cin, Cout, K))
                         it.tc_dgrad = buf("dgrad_tc", n)
                         max_elems = max(max_elems, n)
+                        if name in s2:   # transposed stride-2 conv = two stride-1 convs over even / odd taps
+                            it.tc_dgrad_even = buf("dgrad_tc_even", int(self.lib.avc_tc_packed_floats(Cin, Cout, (K + 1) // 2)))
+                            it.tc_dgrad_odd = buf("dgrad_tc_odd", int(self.lib.avc_tc_packed_floats(Cin, Cout, K // 2)))
             raw = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8).to(self.dev)
             tables[key] = (raw, len(names), max_elems, used)
         raw, n, max_elems, _ = tables[key]
@@ -354,7 +357,16 @@ class Engine:
         if mask is not None:
             assert direct
             d.mask, d.mask_bstride = mask.ptr, mask.bstride
-        if (self.precision == "tf32" and stride == 1 and Cout % 16 == 0 and Lp <= 256 and "dgrad_tc" in self.packed[name]):
+        if (self.precision == "tf32" and stride == 2 and K == 5 and Cout % 16 == 0 and Lp <= 512 and "dgrad_tc_even" in self.packed[name]):
+            # dxp[2v]   = sum_{jj<3} Wd[2jj]   dc[v + jj - 2]   (taps 0,2,4; pad_left 2)
+            # dxp[2v+1] = sum_{jj<2} Wd[2jj+1] dc[v + jj - 1]   (taps 1,3;   pad_left 1)
+            for par, kk, pl_, key in ((0, 3, 2, "dgrad_tc_even"), (1, 2, 1, "dgrad_tc_odd")):
+                d.K, d.pad_left, d.in_ups = kk, pl_, 1
+                d.Tout = (Lp + 1 - par) // 2
+                d.out_tstride, d.out_toff, d.out_T = 2, par, Lp
+                d.w_tc = self.packed[name][key].data_ptr()
+                self._ck(self.lib.avc_conv_block_tc(C.byref(d), self.tc_status.data_ptr(), st), f"conv_dgrad_tc_s2[{name}]")
+        elif (self.precision == "tf32" and stride == 1 and Cout % 16 == 0 and Lp <= 256 and "dgrad_tc" in self.packed[name]):
             d.w_tc = self.packed[name]["dgrad_tc"].data_ptr()
             self._ck(self.lib.avc_conv_block_tc(C.byref(d), self.tc_status.data_ptr(), st), f"conv_dgrad_tc[{name}]")
         else:

@@ -95,6 +95,8 @@ typedef struct avc_conv_desc {
   /* ---- tensor-core path (avc_conv_block_tc) ---- */
   const float* w_tc; /* weights packed by avc_pack_conv_weight_tc; or null */
   int32_t flags;     /* AVC_F_* */
+  int32_t out_tstride, out_toff, out_T; /* avc_conv_block_tc: out time index = t*out_tstride + out_toff inside an out
+                                          tensor of out_T time steps (0, 0, 0 = dense: index t of Tn) */
 } avc_conv_desc;
 
 /* Fused block forward.  norm=1 needs the whole Tn of a sample inside one CTA tile:
@@ -122,6 +124,8 @@ typedef struct avc_pack_item {
   float* simt_dgrad;  /* AVC_PACK_DGRAD layout for avc_conv_block_fwd, or null */
   float* tc_fwd;      /* avc_pack_conv_weight_tc FWD layout, or null */
   float* tc_dgrad;    /* avc_pack_conv_weight_tc DGRAD layout, or null */
+  float* tc_dgrad_even; /* DGRAD layout restricted to taps 0,2,4,.. (stride-2 transposed conv, even outputs), or null */
+  float* tc_dgrad_odd;  /* ... taps 1,3,.. (odd outputs), or null */
   int32_t Cout, Cin, K, reserved;
 } avc_pack_item;
 int avc_pack_conv_weights_batch(const avc_pack_item* items_dev, int n_items, int64_t max_elems, void* stream);

@@ -153,3 +153,29 @@ def test_tc_wgrad(eng, B, Cin, Cout, K, T):
     eng.wgrad(wd, "t")
     eng.check_tc_status()
     assert relerr(dw.cpu() - 0.25, w.grad) < TOL, relerr(dw.cpu() - 0.25, w.grad)
+
+
+@pytest.mark.parametrize("B,C_,T", [(5, 128, 128), (19, 128, 32), (3, 128, 64)])
+def test_tc_stride2_backward_linear(eng, B, C_, T):
+    """Stride-2 conv (encoder second convs): data gradient as two tap-parity convs and the weight
+    gradient with parity-split staging, both on tcgen05, vs autograd of the plain conv."""
+    K = 5
+    x = rnd((B, C_, T), 1).requires_grad_(True)
+    w = (rnd((C_, C_, K), 2) / math.sqrt(C_ * K)).requires_grad_(True)
+    y = orc.reflect_conv1d(x, w, None, 2)
+    dy = rnd(tuple(y.shape), 3)
+    y.backward(dy)
+    P = {"speaker_encoder.second_conv_layers.1.weight": w.detach().cuda(), "speaker_encoder.second_conv_layers.1.bias": torch.zeros(C_).cuda()}
+    name = "speaker_encoder.second_conv_layers.1"     # a stride-2 layer of the default config
+    G = {k: torch.zeros_like(v) for k, v in P.items()}
+    eng.packed.pop(name, None)
+    eng.conv_names = lambda: [name]
+    eng.pack_weights(P, need_dgrad=True)
+    assert "dgrad_tc_even" in eng.packed[name]
+    rec = dict(name=name, xin=to_a4(eng, x.detach()), c=None, stats=None, cond=None, out=None, stride=2, shuffle=False, norm=False,
+               relu=False, K=K, Cin=C_, Cout=C_, Tout=y.shape[-1], pl=2, pr=2)
+    n0 = __import__("adaptive_voice_conversion_b200._lib", fromlist=["x"]).launch_count()
+    dx = eng.conv_bwd(P, G, rec, to_a4(eng, dy))
+    eng.check_tc_status()
+    assert relerr(from_a4(eng, dx), x.grad) < TOL, relerr(from_a4(eng, dx), x.grad)
+    assert relerr(G[name + ".weight"], w.grad) < TOL, relerr(G[name + ".weight"], w.grad)
