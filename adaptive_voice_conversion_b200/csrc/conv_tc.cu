@@ -58,10 +58,11 @@ __device__ __forceinline__ void quad_transpose(float& a0, float& a1, float& a2, 
   }
 }
 
-__global__ void __launch_bounds__(256, 1) conv_block_tc_kernel(const TcArgs a) {
+__global__ void __launch_bounds__(512, 1) conv_block_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_full[TC_MAX_STAGES], bar_ready[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_done;
   __shared__ uint32_t tmem_slot;
+  __shared__ float2 ep_stat[4][128];  // partial InstanceNorm sums of the 4 epilogue warp groups
   const avc_conv_desc& d = a.d;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b0 = blockIdx.x * a.G;
@@ -208,7 +209,10 @@ __global__ void __launch_bounds__(256, 1) conv_block_tc_kernel(const TcArgs a) {
   ok = __syncthreads_and(ok) != 0;  // block-uniform: the TMEM loads below are .sync.aligned
   tc::tc_fence_after();
   if (a.dbg && tid == 64) tm1 = clock64();
-  const int etid = tid & 127, ewarp = warp & 3, egrp = warp >> 2;  // 8 epilogue warps: 2 per TMEM lane quarter
+  // 16 epilogue warps = 4 groups x 4 TMEM lane quarters.  A group takes one (sample, column part):
+  // with fewer than 4 samples per CTA the columns of a sample are split between groups and the
+  // InstanceNorm partial sums are merged through shared memory.
+  const int etid = tid & 127, ewarp = warp & 3, egrp = warp >> 2;
   const int co = mtile * 128 + etid;  // conv output row of this thread
   const bool co_ok = co < d.Cout;
   if (ok) {
@@ -226,12 +230,18 @@ __global__ void __launch_bounds__(256, 1) conv_block_tc_kernel(const TcArgs a) {
     const int sshift = d.stride == 2 ? 1 : 0, smask = sshift;
     const int ots = d.out_tstride > 0 ? d.out_tstride : 1, oto = d.out_toff;  // out time index = t*ots + oto
     const int ncol = d.stride == 2 ? min(a.npad, 2 * d.Tout) : d.Tout;  // TMEM columns that matter
-    for (int g = egrp; g < nsamp; g += 2) {
+    const int nsplit = nsamp >= 3 ? 1 : (nsamp == 2 ? 2 : 4);
+    const int items = nsamp * nsplit, nchunk = a.npad >> 4;
+    for (int it0 = 0; it0 < items; it0 += 4) {
+      const int item = it0 + egrp;
+      const bool active = item < items;
+      const int g = active ? item / nsplit : 0, part = active ? item - g * nsplit : 0;
+      const int cbeg = active ? (part * nchunk / nsplit) << 4 : 0, cend = active ? ((part + 1) * nchunk / nsplit) << 4 : 0;
       const int b = b0 + g;
       float mean = 0.f, rstd = 1.f;
       if (d.norm) {
         float s1 = 0.f, s2 = 0.f;
-        for (int c0 = 0; c0 < a.npad; c0 += 16) {
+        for (int c0 = cbeg; c0 < cend; c0 += 16) {
           float v[16];
           tc::tmem_ld16(lane_addr + (uint32_t)(g * a.npad + c0), v);
 #pragma unroll
@@ -242,6 +252,15 @@ __global__ void __launch_bounds__(256, 1) conv_block_tc_kernel(const TcArgs a) {
               s2 = fmaf(x, x, s2);
             }
         }
+        ep_stat[egrp][etid] = make_float2(s1, s2);
+        __syncthreads();
+        s1 = 0.f; s2 = 0.f;
+        const int grp0 = egrp - part;  // first group working on this sample
+        for (int p2 = 0; p2 < nsplit; ++p2) {
+          const float2 ps = ep_stat[(grp0 + p2) & 3][etid];
+          s1 += ps.x; s2 += ps.y;
+        }
+        __syncthreads();   // ep_stat is reused by the next batch of items
         if (shuf) {  // rows (2c, 2c+1) pool into normalized channel c
           s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
           s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
@@ -250,11 +269,12 @@ __global__ void __launch_bounds__(256, 1) conv_block_tc_kernel(const TcArgs a) {
         mean = s1 * inv;
         const float var = fmaxf(s2 * inv - mean * mean, 0.f);
         rstd = rsqrtf(var + d.eps);
-        if (d.stats && co_ok && sx_ == 0) {
+        if (d.stats && co_ok && sx_ == 0 && active && part == 0) {
           d.stats[((size_t)b * Cn + cn) * 2 + 0] = mean;
           d.stats[((size_t)b * Cn + cn) * 2 + 1] = rstd;
         }
       }
+      if (!active) continue;
       float beta = 0.f, gamma = 1.f;
       if (d.cond && co_ok) {
         beta = __ldg(d.cond + (size_t)b * d.cond_bstride + cn);
@@ -270,7 +290,7 @@ __global__ void __launch_bounds__(256, 1) conv_block_tc_kernel(const TcArgs a) {
       float* outp = d.out + (size_t)b * d.out_bstride + ((size_t)(cn >> 2) * Tn) * 4 + (cn & 3);
       const float* resp = d.res ? d.res + (size_t)b * d.res_bstride + ((size_t)(cn >> 2) * d.res_T) * 4 + (cn & 3) : nullptr;
       const float* maskp = d.mask ? d.mask + (size_t)b * d.mask_bstride + ((size_t)(cn >> 2) * Tn) * 4 + (cn & 3) : nullptr;
-      for (int c0 = 0; c0 < a.npad; c0 += 16) {
+      for (int c0 = cbeg; c0 < cend; c0 += 16) {
         float v[16];
         tc::tmem_ld16(lane_addr + (uint32_t)(g * a.npad + c0), v);
 #pragma unroll
@@ -508,7 +528,7 @@ extern "C" int avc_conv_block_tc(const avc_conv_desc* d, int* status, void* stre
     attr_smem = smem_max;
   }
   dim3 grid(cdiv(d->B, G), mtiles);
-  conv_block_tc_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a);
+  conv_block_tc_kernel<<<grid, 512, smem, (cudaStream_t)stream>>>(a);
   AVC_CHECK_LAUNCH("conv_block_tc");
   return AVC_OK;
 }
