@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
   const uint32_t idesc = tc::make_idesc_tf32(128, a.ntpad, 1, 1);
   const int nq_x = a.ntpad >> 2;  // 16-byte units per row of the x operand
   bool ok = true;
-  bool first = true;
+  const uint32_t smem_base = tc::smem_u32(smem);
 
   for (int tile = tile0; tile < tile1; ++tile) {
     const int it = tile - tile0;
@@ -117,26 +117,37 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     tc::fence_proxy_async_smem();
     ok = __syncthreads_and(ok) != 0;  // also makes `ok` block-uniform for the issue loop below
-    if (warp == 0 && ok) {  // warp-converged issue loop, one elected lane per instruction (uniform descriptors)
-      tc::tc_fence_after();
-      const uint32_t a_lo0 = tc::sdesc_lo(tc::smem_u32(sA), atomA), b_lo0 = tc::sdesc_lo(tc::smem_u32(sX), atomX);
-      const uint32_t hi = tc::sdesc_hi(512, 1);
-      for (int g = 0; g < nsamp; ++g)
-        for (int ks = 0; ks < T / 8; ++ks) {
-          const uint32_t a_lo = a_lo0 + (uint32_t)(g * T + 8 * ks) * 8u;         // rows * 128 B >> 4
-          const uint32_t b_base = b_lo0 + (uint32_t)((S == 1 ? g * TX : g * 2 * H) + 8 * ks) * 8u;
-          uint32_t dcol = tbase;
-          const uint32_t acc = (first && g == 0 && ks == 0) ? 0u : 1u;
-          for (int j = 0; j < K; ++j) {
-            const uint32_t b_lo = b_base + (uint32_t)(S == 1 ? j : (j & 1) * H + (j >> 1)) * 8u;
-            if (tc::elect_one()) tc::mma_tf32_lohi(dcol, a_lo, hi, b_lo, hi, idesc, acc);
-            dcol += (uint32_t)a.ntpad;
+    if (warp == 0) {  // warp-converged issue loop, one elected lane per instruction (uniform descriptors)
+      if (__all_sync(0xffffffffu, ok)) {
+        tc::tc_fence_after();
+        const uint32_t sbase = smem_base + (uint32_t)buf * a.buf_bytes;
+        const uint32_t a_lo0 = tc::sdesc_lo(sbase, atomA), b_lo0 = tc::sdesc_lo(sbase + a.x_off, atomX);
+        const uint32_t hi = tc::sdesc_hi(512, 1);
+        for (int g = 0; g < nsamp; ++g)
+          for (int ks = 0; ks < T / 8; ++ks) {
+            const uint32_t a_lo = a_lo0 + (uint32_t)(g * T + 8 * ks) * 8u;         // rows * 128 B >> 4
+            const uint32_t b_base = b_lo0 + (uint32_t)((S == 1 ? g * TX : g * 2 * H) + 8 * ks) * 8u;
+            uint32_t dcol = tbase;
+            const uint32_t acc = (it == 0 && g == 0 && ks == 0) ? 0u : 1u;
+            if (S == 1) {
+              uint32_t b_lo = b_base;
+              for (int j = 0; j < K; ++j) {
+                if (tc::elect_one()) tc::mma_tf32_lohi(dcol, a_lo, hi, b_lo, hi, idesc, acc);
+                b_lo += 8u;
+                dcol += (uint32_t)a.ntpad;
+              }
+            } else {
+              for (int j = 0; j < K; ++j) {
+                const uint32_t b_lo = b_base + (uint32_t)((j & 1) * H + (j >> 1)) * 8u;
+                if (tc::elect_one()) tc::mma_tf32_lohi(dcol, a_lo, hi, b_lo, hi, idesc, acc);
+                dcol += (uint32_t)a.ntpad;
+              }
+            }
           }
-        }
-      __syncwarp();
-      if (tc::elect_one()) tc::mma_commit(&bar_free[buf]);
+        __syncwarp();
+        if (tc::elect_one()) tc::mma_commit(&bar_free[buf]);
+      }
     }
-    first = false;
   }
   if (warp == 0) {
     __syncwarp();

@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="train", choices=["train", "inference"],
+                    help="train: BASELINE config 3/4 (default, the headline metric); inference: config 5, 64 (src,tgt) pairs of 80x512")
     return ap.parse_args()
 
 
@@ -310,8 +312,60 @@ def run_b200(args):
         torch.distributed.destroy_process_group()
 
 
+def run_inference(args):
+    """BASELINE config 5: one-shot VC on 64 synthetic (src, tgt) 80-mel utterance pairs of 512
+    frames through Inferencer.inference_batch; utterances/s, device-resident and e2e (host pairs)."""
+    import types
+    import oracle.ae_oracle as orc
+    from adaptive_voice_conversion_b200.inference import Inferencer
+    dev = torch.device("cuda", 0)
+    cfg = config_for(args.c_in, 64)
+    inf = Inferencer(cfg, types.SimpleNamespace(attr=None, model=None, source=None, target=None, output=None, sample_rate=24000))
+    g = torch.Generator().manual_seed(3)
+    xs = torch.randn((64, args.c_in, 512), generator=g).pin_memory()
+    xc = torch.randn((64, args.c_in, 512), generator=g).pin_memory()
+    xd, cd = xs.to(dev), xc.to(dev)
+    K, W = args.steps, max(args.warmup, 3)
+    for _ in range(W):
+        out = inf.inference_batch(xd, cd)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        out = inf.inference_batch(xd, cd)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(K):
+        host = inf.inference_batch(xs.to(dev, non_blocking=True), xc.to(dev, non_blocking=True)).cpu()
+    f1.record()
+    torch.cuda.synchronize()
+    ms2 = f0.elapsed_time(f1)
+    line = {"metric": "inference utts/sec (one-shot VC, 80-mel x 512-frame pairs)", "value": 64 * K / (ms * 1e-3), "unit": "utterances/s",
+            "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic N(0,1) mels, random-init weights",
+            "config": {"workload": "AE.inference, 64 (src,tgt) pairs of 80x512 (BASELINE config 5)", "global_batch": 64},
+            "e2e": {"value": 64 * K / (ms2 * 1e-3), "unit": "utterances/s", "h2d_bytes_per_step": 2 * xs.numel() * 4, "d2h_bytes_per_step": host.numel() * 4},
+            "precision": inf.model.engine(dev).precision}
+    if not args.skip_cpu:
+        torch.set_num_threads(min(16, os.cpu_count() or 1))
+        sd = orc.init_state(cfg, seed=0)
+        with torch.no_grad():
+            orc.ae_inference(sd, cfg, xs[:8], xc[:8])
+            t0 = time.perf_counter()
+            orc.ae_inference(sd, cfg, xs, xc)
+            dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": 64 / dt, "unit": "utterances/s", "cores": min(16, os.cpu_count() or 1), "kind": "port",
+                                "sample": "one batched pass over the 64 pairs (oracle port, torch CPU fp32)"}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
+    if args.workload == "inference" and args.impl != "reference":
+        return run_inference(args)
     if args.impl == "reference":
         run_reference(args)
     else:
