@@ -436,6 +436,8 @@ class Engine:
         for i, _k in enumerate(ks):
             _, r = self.conv(P, f"{enc}.conv_bank.{i}", x4, relu=True, out=cat.channels(i * c_bank, (i + 1) * c_bank), train=False)
             recs.append(r)
+        # every writer of `cat` (pack_a4 and the bank convs' epilogues) rounds to TF32 in tf32 mode
+        cat.tf32 = self.precision == "tf32"
         out, rec_in = self.conv(P, f"{enc}.in_conv_layer", cat, norm=norm, relu=True, train=train)
         if train:
             ctx["cat"], ctx["x4"], ctx["in"] = cat, x4, rec_in
