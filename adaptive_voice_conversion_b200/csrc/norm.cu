@@ -245,6 +245,91 @@ __global__ void __launch_bounds__(256) norm_bwd_kernel(const avc_conv_desc d) {
   }
 }
 
+// norm_bwd for the common training shape (no pixel shuffle, Tout <= 128): the row of `c` and of
+// `dy` is read ONCE into registers (4 float4 each per lane) and reused by both passes.
+__global__ void __launch_bounds__(256) norm_bwd_cached_kernel(const avc_conv_desc d) {
+  const int Cn = d.Cout, Tn = d.Tout, Cnq = Cn >> 2;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= d.B * Cnq) return;
+  const int b = warp / Cnq, qn = warp - b * Cnq;
+  const float* cb = d.save_c + (int64_t)b * d.Cout * d.Tout + (int64_t)qn * d.Tout * 4;
+  const float* dyb = d.dy + (int64_t)b * d.dy_bstride + (int64_t)qn * Tn * 4;
+  float mean[4] = {0, 0, 0, 0}, rstd[4] = {1, 1, 1, 1}, beta[4] = {0, 0, 0, 0}, gamma[4] = {1, 1, 1, 1};
+  if (d.norm) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      mean[c] = __ldg(d.stats + ((int64_t)b * Cn + qn * 4 + c) * 2 + 0);
+      rstd[c] = __ldg(d.stats + ((int64_t)b * Cn + qn * 4 + c) * 2 + 1);
+    }
+  }
+  if (d.cond) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      beta[c] = __ldg(d.cond + (int64_t)b * d.cond_bstride + qn * 4 + c);
+      gamma[c] = __ldg(d.cond + (int64_t)b * d.cond_bstride + Cn + qn * 4 + c);
+    }
+  }
+  float xv[4][4], gv[4][4];   // [iteration][channel]: xhat (or c when !norm) and the ReLU-masked dy
+  float s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int t = lane + 32 * it;
+    float4 c4 = zero4(), g4 = zero4();
+    if (t < d.Tout) {
+      c4 = ldg4(cb + (int64_t)t * 4);
+      g4 = ldg4(dyb + (int64_t)t * 4);
+    }
+    const float cc[4] = {c4.x, c4.y, c4.z, c4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float xh = d.norm ? (cc[c] - mean[c]) * rstd[c] : cc[c];
+      const float pre = d.norm ? fmaf(xh, gamma[c], beta[c]) : cc[c];
+      const float g = (t < d.Tout && !(d.relu && !(pre > 0.f))) ? gg[c] : 0.f;
+      xv[it][c] = xh;
+      gv[it][c] = g;
+      s0[c] += g;
+      s1[c] += g * xh;
+    }
+  }
+  if (d.norm) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      s0[c] = warp_sum(s0[c]);
+      s1[c] = warp_sum(s1[c]);
+    }
+    if (d.dcond && lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        d.dcond[(int64_t)b * d.dcond_bstride + qn * 4 + c] = s0[c];
+        d.dcond[(int64_t)b * d.dcond_bstride + Cn + qn * 4 + c] = s1[c];
+      }
+    }
+  }
+  const float invT = 1.f / (float)Tn;
+  float db[4] = {0, 0, 0, 0};
+  float* dcb = d.dc + (int64_t)b * d.Cout * d.Tout + (int64_t)qn * d.Tout * 4;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int t = lane + 32 * it;
+    float o[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float dv = d.norm ? rstd[c] * gamma[c] * (gv[it][c] - invT * s0[c] - xv[it][c] * invT * s1[c]) : gv[it][c];
+      db[c] += (t < d.Tout) ? dv : 0.f;
+      o[c] = (d.flags & AVC_F_ROUND_OUT) ? rna_tf32(dv) : dv;
+    }
+    if (t < d.Tout) st4(dcb + (int64_t)t * 4, make_float4(o[0], o[1], o[2], o[3]));
+  }
+  if (d.dbias) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float s = warp_sum(db[c]);
+      if (lane == 0) atomicAdd(d.dbias + qn * 4 + c, s);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) fold_add_kernel(const avc_fold_desc d) {
   const int Cq = d.C >> 2;
   const int64_t total = (int64_t)d.B * Cq * d.Tin;
@@ -338,6 +423,7 @@ extern "C" int avc_norm_bwd(const avc_conv_desc* d, void* stream) {
   const int64_t warps = (int64_t)d->B * (Cn / 4);
   const int blocks = (int)cdiv64(warps * 32, 256);
   if (d->shuffle) norm_bwd_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(*d);
+  else if (d->Tout <= 128) norm_bwd_cached_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*d);
   else norm_bwd_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(*d);
   AVC_CHECK_LAUNCH("norm_bwd");
   return AVC_OK;
