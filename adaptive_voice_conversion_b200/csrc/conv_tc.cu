@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc_kernel(const TcArgs a) {
   const int mtile = blockIdx.y;
   const int nsamp = min(a.G, d.B - b0);
   const int K = d.K;
-  const int xrows = a.G * a.rows + 8;             // rows of one chunk plane in a stage (+ tap-shift slack)
+  const int xrows = a.G * a.rows;                 // rows of one chunk plane in a stage
   const uint32_t x_chunk_bytes = (uint32_t)xrows * 16u;
 
   if (tid == 0) {
@@ -119,9 +119,7 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc_kernel(const TcArgs a) {
     // elected lane executes each tcgen05 instruction: descriptors then live in uniform registers.
     // (Issuing from inside `if (lane == 0)` made ptxas wrap every UTCHMMA in an ELECT + 5x
     // R2UR.BROADCAST waterfall: measured 144 cycles per MMA.)
-    const int ntot = nsamp * a.rows;   // stacked columns of this CTA (multiple of 16)
-    const uint32_t idesc256 = tc::make_idesc_tf32(128, 256, 0, 0);
-    const uint32_t idesc_tail = tc::make_idesc_tf32(128, (ntot & 255) ? (ntot & 255) : 256, 0, 0);
+    const uint32_t idesc = tc::make_idesc_tf32(128, a.npad, 0, 0);
     const uint32_t d_hi = tc::sdesc_hi(128);
     const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
     const uint32_t smem0 = tc::smem_u32(smem);
@@ -138,18 +136,17 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc_kernel(const TcArgs a) {
       const uint32_t sx = sw + a.w_bytes;
       const uint32_t a_lo0 = tc::sdesc_lo(sw, 2048), b_lo0 = tc::sdesc_lo(sx, x_chunk_bytes);
       const uint32_t ks_b = 2u * (x_chunk_bytes >> 4);
-      // The G samples of the CTA are stacked row-wise (pitch a.rows), so an MMA of up to 256
-      // columns may span sample boundaries: the columns that fall on halo rows are garbage and
-      // never read back.  One MMA per (tap, k-step, 256-column tile) instead of one per sample.
       for (int j = 0; j < K; ++j) {
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
           const uint32_t a_lo = a_lo0 + (uint32_t)j * (TC_WTAP_BYTES >> 4) + (uint32_t)ks * (4096 >> 4);
-          const uint32_t b_lo = b_lo0 + (uint32_t)ks * ks_b + (uint32_t)j;
+          uint32_t b_lo = b_lo0 + (uint32_t)ks * ks_b + (uint32_t)j;
+          uint32_t dcol = tb;
           const uint32_t acc = (i | j | ks) ? 1u : 0u;
-          for (int n0 = 0; n0 < ntot; n0 += 256) {
-            const uint32_t id = (ntot - n0 >= 256) ? idesc256 : idesc_tail;
-            if (tc::elect_one()) tc::mma_tf32_lohi(tb + (uint32_t)n0, a_lo, d_hi, b_lo + (uint32_t)n0, d_hi, id, acc);
+          for (int g = 0; g < nsamp; ++g) {
+            if (tc::elect_one()) tc::mma_tf32_lohi(dcol, a_lo, d_hi, b_lo, d_hi, idesc, acc);
+            b_lo += (uint32_t)a.rows;
+            dcol += (uint32_t)a.npad;
           }
         }
       }
@@ -498,10 +495,9 @@ extern "C" int avc_conv_block_tc(const avc_conv_desc* d, int* status, void* stre
   if (!a.d.res) a.d.res_mode = AVC_RES_NONE;
   a.status = status;
   a.dbg = g_tc_dbg;
-  // per-sample pitch (shared-memory rows AND TMEM columns): conv columns + halo, multiple of 16
-  a.rows = (ncols_full + d->K - 1 + 15) / 16 * 16;
-  if (a.rows < (d->Tin + d->pad_left + 15) / 16 * 16) a.rows = (d->Tin + d->pad_left + 15) / 16 * 16;  // all data rows must fit
-  a.npad = a.rows;
+  a.npad = (ncols_full + 15) / 16 * 16;
+  a.rows = a.npad + d->K - 1;
+  if (a.rows < d->Tin + d->pad_left) a.rows = d->Tin + d->pad_left;  // all data rows must fit
   a.nslab = d->Cin / TC_SLAB;
   a.w_bytes = (uint32_t)d->K * TC_WTAP_BYTES;
   const int mtiles = cdiv(d->Cout, 128);
@@ -510,7 +506,7 @@ extern "C" int avc_conv_block_tc(const avc_conv_desc* d, int* status, void* stre
   if (G > gmax_tmem) G = gmax_tmem;
   if (G < 1) G = 1;
   const int smem_max = 220 * 1024;
-  auto stage_bytes = [&](int g) { return (uint32_t)(a.w_bytes + 4 * (g * a.rows + 8) * 16); };
+  auto stage_bytes = [&](int g) { return (uint32_t)(a.w_bytes + 4 * g * a.rows * 16); };
   while (G > 1 && 2 * stage_bytes(G) > (uint32_t)smem_max) --G;
   AVC_REQUIRE(2 * stage_bytes(G) <= (uint32_t)smem_max, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: tile does not fit shared memory");
   a.G = G;
