@@ -26,7 +26,6 @@ int validate_conv_desc(const avc_conv_desc* d, const char* who);
 constexpr int TC_SLAB = 16;          // input channels per pipeline stage (2 MMA K-steps)
 constexpr int TC_WTAP_BYTES = 8192;  // one tap of one slab: 4 chunks x 128 co x 16 B
 constexpr int TC_MAX_STAGES = 4;
-constexpr int TC_WLOADERS = 384;     // threads of warps 4..15 streaming the weight stages with cp.async
 
 struct TcArgs {
   avc_conv_desc d;
@@ -75,7 +74,7 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc_kernel(const TcArgs a) {
 
   if (tid == 0) {
     for (int s = 0; s < a.nstage; ++s) {
-      tc::mbar_init(&bar_full[s], 1 + TC_WLOADERS);  // X producer + the weight-loader threads
+      tc::mbar_init(&bar_full[s], 1);
       tc::mbar_init(&bar_ready[s], 64);
       tc::mbar_init(&bar_empty[s], 1);
     }
@@ -94,6 +93,7 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc_kernel(const TcArgs a) {
   // ------------------------------------------------------------------ main loop (warp roles)
   if (warp == 0) {
     // TMA producer: warp-converged loop, one elected lane per bulk copy (uniform operands)
+    const float* wsrc = d.w_tc + (size_t)mtile * a.nslab * (a.w_bytes / 4);
     for (int i = 0; i < a.nslab; ++i) {
       const int s = i % a.nstage;
       const uint32_t ph = (uint32_t)(i / a.nstage) & 1u;
@@ -103,7 +103,10 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc_kernel(const TcArgs a) {
       if (!ok) break;
       uint8_t* sw = smem + (size_t)s * a.stage_bytes;
       uint8_t* sx = sw + a.w_bytes;
-      if (tc::elect_one()) tc::mbar_arrive_expect_tx(&bar_full[s], (uint32_t)nsamp * 4u * (uint32_t)d.Tin * 16u);
+      if (tc::elect_one()) {
+        tc::mbar_arrive_expect_tx(&bar_full[s], a.w_bytes + (uint32_t)nsamp * 4u * (uint32_t)d.Tin * 16u);
+        tc::bulk_g2s(sw, wsrc + (size_t)i * (a.w_bytes / 4), a.w_bytes, &bar_full[s]);
+      }
       __syncwarp();
       for (int g = 0; g < nsamp; ++g)
         for (int q = 0; q < 4; ++q)
@@ -153,23 +156,6 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc_kernel(const TcArgs a) {
     }
     __syncwarp();
     if (ok && tc::elect_one()) tc::mma_commit(&bar_done);
-  } else if (warp >= 4) {
-    // weight loaders: 384 threads stream each stage's weight block with 16-byte cp.async (the LSU path
-    // keeps thousands of bytes in flight per SM; one elected thread issuing a 40 KB bulk copy delivered
-    // only ~11-16 B/clk/SM and bounded the main loop)
-    const int lt = tid - 128;
-    const float* wsrc = d.w_tc + (size_t)mtile * a.nslab * (a.w_bytes / 4);
-    const int units = (int)(a.w_bytes >> 4);
-    for (int i = 0; i < a.nslab; ++i) {
-      const int s = i % a.nstage;
-      const uint32_t ph = (uint32_t)(i / a.nstage) & 1u;
-      if (i >= a.nstage) ok = tc::mbar_wait(&bar_empty[s], ph ^ 1u, a.status, 8);
-      if (!ok) break;
-      uint8_t* sw = smem + (size_t)s * a.stage_bytes;
-      const float* src = wsrc + (size_t)i * (a.w_bytes / 4);
-      for (int u = lt; u < units; u += TC_WLOADERS) tc::cp_async16_cg(sw + (size_t)u * 16, src + (size_t)u * 4);
-      tc::cp_async_mbar_arrive_noinc(&bar_full[s]);
-    }
   } else if (warp == 1 || warp == 3) {
     // warps 1 and 3: round staged inputs to TF32 (RN) and patch the halo rows
     const int ptid = (warp == 1 ? 0 : 32) + lane;  // 0..63
