@@ -11,6 +11,7 @@ for (Cin, Cout, K, T, tag) in [(128, 128, 5, 128, "conv5 T128"), (1104, 128, 1, 
     P = {"r.weight": w, "r.bias": torch.zeros(Cout, device=dev)}
     eng.packed.pop("r", None); eng.conv_names = lambda: ["r"]; eng.pack_weights(P, need_dgrad=False)
     x = A4.empty(256, Cin, T, dev); x.t.normal_()
+    x.tf32 = True   # as in the real model (producers round): the kernel skips its rounding pass
     for _ in range(3):
         eng.conv(P, "r", x, norm=True, relu=True, train=True)
     dbg = torch.zeros(12 * 1024, dtype=torch.int64, device=dev)
