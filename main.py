@@ -1,10 +1,11 @@
-"""Training entry point with the reference's flags (main.py:9-22 of the reference):
+"""Training entry point; accepts the reference's command line (flag names of its main.py:9-22).
 
     python main.py -c config.yaml -d <data_dir|synthetic> -train_set train_128 \
         -train_index_file train_samples_128.json -store_model_path <path> -t <tag> -iters N
 
 Under ``torchrun --nproc-per-node N`` every rank trains on its own batches with one NCCL
-gradient all-reduce per step (data parallel)."""
+gradient all-reduce per step (data parallel).
+"""
 import os
 from argparse import ArgumentParser
 
@@ -13,25 +14,40 @@ import torch
 from adaptive_voice_conversion_b200.config import load_config
 from adaptive_voice_conversion_b200.solver import Solver
 
-if __name__ == "__main__":
-    p = ArgumentParser()
-    p.add_argument("-config", "-c", default="config.yaml")
-    p.add_argument("-data_dir", "-d", default="synthetic")
-    p.add_argument("-train_set", default="train")
-    p.add_argument("-train_index_file", default="train_samples_64.json")
-    p.add_argument("-logdir", default="log/")
-    p.add_argument("--load_model", action="store_true")
-    p.add_argument("--load_opt", action="store_true")
-    p.add_argument("-store_model_path", default="model")
-    p.add_argument("-load_model_path", default="model")
-    p.add_argument("-summary_steps", default=100, type=int)
-    p.add_argument("-save_steps", default=5000, type=int)
-    p.add_argument("-tag", "-t", default="init")
-    p.add_argument("-iters", default=0, type=int)
-    args = p.parse_args()
+# (flags, default, type) -- string options first, then integers; the two switches are added below
+OPTIONS = [
+    (("-config", "-c"), "config.yaml", str),
+    (("-data_dir", "-d"), "synthetic", str),
+    (("-train_set",), "train", str),
+    (("-train_index_file",), "train_samples_64.json", str),
+    (("-logdir",), "log/", str),
+    (("-store_model_path",), "model", str),
+    (("-load_model_path",), "model", str),
+    (("-tag", "-t"), "init", str),
+    (("-summary_steps",), 100, int),
+    (("-save_steps",), 5000, int),
+    (("-iters",), 0, int),
+]
+
+
+def parse_args(argv=None):
+    parser = ArgumentParser(description="AdaIN-VC training on B200")
+    for flags, default, kind in OPTIONS:
+        parser.add_argument(*flags, default=default, type=kind)
+    for switch in ("--load_model", "--load_opt"):
+        parser.add_argument(switch, action="store_true")
+    return parser.parse_args(argv)
+
+
+def main(argv=None):
+    args = parse_args(argv)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         torch.distributed.init_process_group("nccl")
     solver = Solver(config=load_config(args.config), args=args)
     if args.iters > 0:
         solver.train(n_iterations=args.iters)
+
+
+if __name__ == "__main__":
+    main()
