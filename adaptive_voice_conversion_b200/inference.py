@@ -63,6 +63,7 @@ class Inferencer(object):
         """x, x_cond: [T, n_mels] normalised mels on the device (inference.py:62-70)."""
         dec = self.model.inference(self.utt_make_frames(x), self.utt_make_frames(x_cond))
         dec = dec.transpose(1, 2).squeeze(0).detach().cpu().numpy()
+        self.model.engine(x.device).check_tc_status()
         if self.attr is not None:
             dec = self.denormalize(dec)
         wav = self.vocoder.melspectrogram2wav(dec) if self.vocoder is not None else None

@@ -122,4 +122,5 @@ class FusedTrainer:
         """(loss_rec, loss_kl, grad_norm) as Python floats -- synchronises."""
         s = self.sums.tolist()
         gn = float(self.opt.grad_norm().item())
+        self.eng.check_tc_status()   # a tcgen05 pipeline barrier time-out must not go unnoticed
         return s[0] / self.n_rec, 0.5 * s[1] / self.n_lat, gn

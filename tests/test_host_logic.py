@@ -60,3 +60,34 @@ def test_collate_and_synthetic_loader():
     it = iter(SyntheticSegments(4, 80, 128, seed=3))
     a, b = next(it), next(it)
     assert a.shape == (4, 80, 128) and not torch.equal(a, b)
+
+
+def test_bench_reference_arm_schema():
+    """`bench.py --impl reference` (the CPU oracle port timed on the host) prints ONE JSON line
+    with the contract's keys; runs without a GPU."""
+    import json, subprocess, sys, os
+    from conftest import ROOT
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="8"))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_cli_flags_match_reference_names():
+    """main.py keeps the reference's flag names (main.py:9-22 of the reference)."""
+    import importlib.util, os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("avc_main", os.path.join(ROOT, "main.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    a = m.parse_args(["-c", "x.yaml", "-d", "dd", "-train_set", "tr", "-train_index_file", "i.json", "-logdir", "l", "--load_model",
+                      "-store_model_path", "s", "-load_model_path", "p", "-summary_steps", "7", "-save_steps", "9", "-t", "tag", "-iters", "3"])
+    assert (a.config, a.data_dir, a.train_set, a.train_index_file, a.load_model, a.load_opt, a.summary_steps, a.iters, a.tag) == \
+           ("x.yaml", "dd", "tr", "i.json", True, False, 7, 3, "tag")
