@@ -32,7 +32,12 @@ class FusedTrainer:
         self.G: Dict[str, torch.Tensor] = opt.named_grad_views(model)
         self.pg = process_group
         self.world = opt.world_size
-        self.sums = torch.zeros(2, dtype=torch.float32, device=self.dev)
+        # one 16-byte report block so that reading a step's scalars is ONE device->host copy:
+        # [sum|dec-x|, sum KL terms, sum g^2, tcgen05 status word]
+        self.report = torch.zeros(4, dtype=torch.float32, device=self.dev)
+        self.sums = self.report[0:2]
+        opt.sqnorm = self.report[2:3]
+        self.eng.tc_status = self.report[3:4].view(torch.int32)
         self.n_rec = 1
         self.n_lat = 1
         self._graphs = None
@@ -120,7 +125,9 @@ class FusedTrainer:
 
     def losses(self):
         """(loss_rec, loss_kl, grad_norm) as Python floats -- synchronises."""
-        s = self.sums.tolist()
-        gn = float(self.opt.grad_norm().item())
-        self.eng.check_tc_status()   # a tcgen05 pipeline barrier time-out must not go unnoticed
-        return s[0] / self.n_rec, 0.5 * s[1] / self.n_lat, gn
+        import struct
+        r = self.report.tolist()     # the only synchronisation of a step
+        status = struct.unpack("<i", struct.pack("<f", r[3]))[0]
+        if status != 0:              # a tcgen05 pipeline barrier time-out must not go unnoticed
+            raise L.AvcError(f"tcgen05 conv pipeline barrier timed out (code {status})")
+        return r[0] / self.n_rec, 0.5 * r[1] / self.n_lat, (r[2] ** 0.5) / self.world
