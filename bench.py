@@ -293,7 +293,7 @@ def run_b200(args):
                        "global_batch": B * world, "per_gpu_batch": B, "c_in": args.c_in, "parallelism": f"dp{world}",
                        "cuda_graph": not args.no_graph,
                        "l2": "per-step working set (~1.5 GB saved activations) >> 126 MB L2; no explicit flush"},
-            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": B * args.c_in * SEG_T * 4, "d2h_bytes_per_step": 12,
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": B * args.c_in * SEG_T * 4, "d2h_bytes_per_step": 16,
                     "api": "Solver.ae_step(pinned host batch, lambda_kl) -> {'loss_rec','loss_kl','grad_norm'}"},
             "gpu_launches": int(launches_per_step) * K,
             "launches_per_step": int(launches_per_step),
