@@ -62,13 +62,39 @@ def config_for(c_in, batch):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock / power / throttle reasons DURING the timed region.  NVML in-process (about a
+    thousand samples per second); falls back to polling nvidia-smi (a few samples per second)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         self.index, self.rows, self.stop = index, [], threading.Event()
-        self.th = threading.Thread(target=self.run, daemon=True)
+        self.sm, self.power, self.mask, self.sm_max, self.how = [], [], 0, None, "nvidia-smi"
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.how = pynvml, "nvml"
+        except Exception:
+            self.nvml = None
+        self.th = threading.Thread(target=self.run_nvml if self.nvml else self.run_smi, daemon=True)
 
-    def run(self):
+    def run_nvml(self):
+        n = self.nvml
+        reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self.stop.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                self.power.append(n.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                if reasons is not None:
+                    self.mask |= int(reasons(self.h))
+            except Exception:
+                pass
+            self.stop.wait(0.002)
+
+    def run_smi(self):
         while not self.stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
@@ -88,14 +114,20 @@ class ClockSampler:
         self.th.join(timeout=3)
 
     def summary(self):
+        if self.nvml:
+            if not self.sm:
+                return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": 0, "how": self.how}
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "power_w_max": max(self.power) if self.power else None,
+                    "reasons": [name for name, bit in self.REASONS if self.mask & bit], "samples": len(sm), "how": self.how}
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "how": self.how}
         sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
                 "power_w_max": max((float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()), default=None),
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "how": self.how}
 
 
 # ----------------------------------------------------------------------------- CPU arm
