@@ -31,6 +31,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# torchrun exports OMP_NUM_THREADS=1 to every rank; rank 0 also runs the CPU legs (cpu_baseline,
+# --impl reference), which must be free to use the host's cores: clear it BEFORE torch loads.
+if os.environ.get("RANK", "0") == "0":
+    for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.pop(_v, None)
+
 import torch  # noqa: E402
 
 METRIC = "mel-segments/sec (80x128) train step"
