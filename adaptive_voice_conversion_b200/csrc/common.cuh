@@ -14,6 +14,8 @@ namespace avc {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+int opt_tc_uniform_issue();  // runtime options, see avc_set_option
+int opt_wgrad_reduce_v2();
 
 #define AVC_REQUIRE(cond, code, ...) \
   do {                               \

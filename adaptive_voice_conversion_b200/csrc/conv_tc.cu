@@ -58,13 +58,43 @@ __device__ __forceinline__ void quad_transpose(float& a0, float& a1, float& a2, 
   }
 }
 
+// All MMAs of one 16-channel slab: 2 k-steps x nsamp samples x K taps; taps j = 0..K-1 of one
+// (k-step, sample) accumulate into the same TMEM columns.  Called by the whole (converged) issuer
+// warp with warp-uniform arguments.
+template <int KT>
+__device__ __forceinline__ void issue_slab(uint32_t tb, uint32_t a_lo0, uint32_t b_lo0, uint32_t ks_b, uint32_t d_hi, uint32_t idesc,
+                                           uint32_t slab, int nsamp, int rows, int npad, int K) {
+  const int n = KT ? KT : K;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    const uint64_t a_ks = tc::sdesc64(a_lo0 + (uint32_t)ks * (4096 >> 4), d_hi);
+    uint64_t b_g = tc::sdesc64(b_lo0 + (uint32_t)ks * ks_b, d_hi);
+    uint32_t dcol = tb;
+#pragma unroll 2
+    for (int g = 0; g < nsamp; ++g) {
+      uint64_t a_desc = a_ks, b_desc = b_g;
+#pragma unroll
+      for (int j = 0; j < n; ++j) {
+        tc::mma_tf32_elect(dcol, a_desc, b_desc, idesc, (slab | (uint32_t)ks | (uint32_t)j) ? 1u : 0u);
+        a_desc += (uint64_t)(TC_WTAP_BYTES >> 4);
+        b_desc += 1u;
+      }
+      b_g += (uint32_t)rows;
+      dcol += (uint32_t)npad;
+    }
+  }
+}
+
+// UI (uniform issue): warp index via lane-0 broadcast + election inside the MMA asm, see issue_slab.
+// UI = false is the round-1 issue loop (ELECT + VOTEU per MMA), kept selectable with AVC_TC_ISSUE=legacy.
+template <bool UI>
 __global__ void __launch_bounds__(512, 1) conv_block_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_full[TC_MAX_STAGES], bar_ready[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_done;
   __shared__ uint32_t tmem_slot;
   __shared__ float2 ep_stat[4][128];  // partial InstanceNorm sums of the 4 epilogue warp groups
   const avc_conv_desc& d = a.d;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = UI ? tc::warp_idx_sync() : (tid >> 5), lane = tid & 31;
   const int b0 = blockIdx.x * a.G;
   const int mtile = blockIdx.y;
   const int nsamp = min(a.G, d.B - b0);
@@ -136,17 +166,24 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc_kernel(const TcArgs a) {
       const uint32_t sx = sw + a.w_bytes;
       const uint32_t a_lo0 = tc::sdesc_lo(sw, 2048), b_lo0 = tc::sdesc_lo(sx, x_chunk_bytes);
       const uint32_t ks_b = 2u * (x_chunk_bytes >> 4);
-      for (int j = 0; j < K; ++j) {
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const uint32_t a_lo = a_lo0 + (uint32_t)j * (TC_WTAP_BYTES >> 4) + (uint32_t)ks * (4096 >> 4);
-          uint32_t b_lo = b_lo0 + (uint32_t)ks * ks_b + (uint32_t)j;
-          uint32_t dcol = tb;
-          const uint32_t acc = (i | j | ks) ? 1u : 0u;
-          for (int g = 0; g < nsamp; ++g) {
-            if (tc::elect_one()) tc::mma_tf32_lohi(dcol, a_lo, d_hi, b_lo, d_hi, idesc, acc);
-            b_lo += (uint32_t)a.rows;
-            dcol += (uint32_t)a.npad;
+      if constexpr (UI) {
+        // loop order ks -> sample -> tap: the tap loop only advances two loop-carried 64-bit descriptors
+        // (weights: next tap block; input: one row down), ~6 uniform instructions per MMA
+        if (K == 5) issue_slab<5>(tb, a_lo0, b_lo0, ks_b, d_hi, idesc, (uint32_t)i, nsamp, a.rows, a.npad, 5);
+        else issue_slab<0>(tb, a_lo0, b_lo0, ks_b, d_hi, idesc, (uint32_t)i, nsamp, a.rows, a.npad, K);
+      } else {
+        for (int j = 0; j < K; ++j) {
+  #pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t a_lo = a_lo0 + (uint32_t)j * (TC_WTAP_BYTES >> 4) + (uint32_t)ks * (4096 >> 4);
+            uint32_t b_lo = b_lo0 + (uint32_t)ks * ks_b + (uint32_t)j;
+            uint32_t dcol = tb;
+            const uint32_t acc = (i | j | ks) ? 1u : 0u;
+            for (int g = 0; g < nsamp; ++g) {
+              if (tc::elect_one()) tc::mma_tf32_lohi(dcol, a_lo, d_hi, b_lo, d_hi, idesc, acc);
+              b_lo += (uint32_t)a.rows;
+              dcol += (uint32_t)a.npad;
+            }
           }
         }
       }
@@ -520,7 +557,8 @@ extern "C" int avc_conv_block_tc(const avc_conv_desc* d, int* status, void* stre
   const int smem = a.nstage * (int)a.stage_bytes;
   static int attr_smem = 0;
   if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_block_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    cudaError_t e = cudaFuncSetAttribute(conv_block_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_block_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (e != cudaSuccess) {
       set_error("avc_conv_block_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return AVC_ERR_CUDA;
@@ -528,7 +566,8 @@ extern "C" int avc_conv_block_tc(const avc_conv_desc* d, int* status, void* stre
     attr_smem = smem_max;
   }
   dim3 grid(cdiv(d->B, G), mtiles);
-  conv_block_tc_kernel<<<grid, 512, smem, (cudaStream_t)stream>>>(a);
+  if (opt_tc_uniform_issue()) conv_block_tc_kernel<true><<<grid, 512, smem, (cudaStream_t)stream>>>(a);
+  else conv_block_tc_kernel<false><<<grid, 512, smem, (cudaStream_t)stream>>>(a);
   AVC_CHECK_LAUNCH("conv_block_tc");
   return AVC_OK;
 }

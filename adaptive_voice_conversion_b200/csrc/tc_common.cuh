@@ -150,6 +150,24 @@ __device__ __forceinline__ void mma_tf32_lohi(uint32_t d_tmem, uint32_t a_lo, ui
       ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-converged issue: EVERY lane of a converged warp calls this with warp-uniform operands and one
+// elected lane issues the MMA.  With the election inside the asm and the caller's warp index made
+// provably uniform (warp_idx_sync below), ptxas keeps descriptors in uniform registers and emits a bare
+// UTCHMMA -- no ELECT / VOTEU / R2UR per instruction (SASS checked: 15 -> 6 instructions per MMA).
+// 64-bit descriptors are carried by the caller so that advancing one is a UIADD3 pair in place.
+__device__ __forceinline__ void mma_tf32_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t sdesc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+// warp index as a value ptxas can prove warp-uniform (the CUTLASS canonical_warp_idx_sync idiom):
+// role branches on it are uniform branches, code inside them uses the uniform datapath
+__device__ __forceinline__ int warp_idx_sync() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -47,12 +47,14 @@ __device__ __forceinline__ uint32_t mn_unit_off(int q, int row, uint32_t atom_by
   return (uint32_t)(q >> 3) * atom_bytes + (uint32_t)row * 128u + (uint32_t)((((q & 7) >> 1) ^ (row & 3)) << 5) + (uint32_t)((q & 1) << 4);
 }
 
+// UI (uniform issue): see conv_tc.cu; UI = false is the round-1 issue loop
+template <bool UI>
 __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_free[2], bar_done;
   __shared__ uint32_t tmem_slot;
   const avc_wgrad_desc& d = a.d;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = UI ? tc::warp_idx_sync() : (tid >> 5);
   const int ci0 = blockIdx.x * WT_NT, co0 = blockIdx.y * 128, sl = blockIdx.z;
   const int K = d.K, T = d.Tout, TX = a.TX;  // padded input positions per sample
   const int S = d.stride, H = a.H;
@@ -119,31 +121,76 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
     ok = __syncthreads_and(ok) != 0;  // also makes `ok` block-uniform for the issue loop below
     if (warp == 0) {  // warp-converged issue loop, one elected lane per instruction (uniform descriptors)
       if (__all_sync(0xffffffffu, ok)) {
-        tc::tc_fence_after();
-        const uint32_t sbase = smem_base + (uint32_t)buf * a.buf_bytes;
-        const uint32_t a_lo0 = tc::sdesc_lo(sbase, atomA), b_lo0 = tc::sdesc_lo(sbase + a.x_off, atomX);
-        const uint32_t hi = tc::sdesc_hi(512, 1);
-        for (int g = 0; g < nsamp; ++g)
-          for (int ks = 0; ks < T / 8; ++ks) {
-            const uint32_t a_lo = a_lo0 + (uint32_t)(g * T + 8 * ks) * 8u;         // rows * 128 B >> 4
-            const uint32_t b_base = b_lo0 + (uint32_t)((S == 1 ? g * TX : g * 2 * H) + 8 * ks) * 8u;
-            uint32_t dcol = tbase;
-            const uint32_t acc = (it == 0 && g == 0 && ks == 0) ? 0u : 1u;
-            if (S == 1) {
-              uint32_t b_lo = b_base;
-              for (int j = 0; j < K; ++j) {
-                if (tc::elect_one()) tc::mma_tf32_lohi(dcol, a_lo, hi, b_lo, hi, idesc, acc);
-                b_lo += 8u;
-                dcol += (uint32_t)a.ntpad;
+        if constexpr (UI) {
+          tc::tc_fence_after();
+          // everything the MMAs consume is re-derived from lane-0 broadcasts: ptxas then proves the
+          // values warp-uniform and keeps the whole issue loop on the uniform datapath
+          const int it_u = __shfl_sync(0xffffffffu, it, 0), nsamp_u = __shfl_sync(0xffffffffu, nsamp, 0);
+          const uint32_t tb_u = __shfl_sync(0xffffffffu, tbase, 0);
+          const uint32_t sbase = __shfl_sync(0xffffffffu, smem_base, 0) + (uint32_t)(it_u & 1) * a.buf_bytes;
+          const uint32_t a_lo0 = tc::sdesc_lo(sbase, atomA), b_lo0 = tc::sdesc_lo(sbase + a.x_off, atomX);
+          const uint32_t hi = tc::sdesc_hi(512, 1);
+          const int nks = T >> 3;
+          for (int g = 0; g < nsamp_u; ++g) {
+            // loop-carried 64-bit descriptors: one k-step = 8 rows = 64 descriptor units on both operands
+            uint64_t a_desc = tc::sdesc64(a_lo0 + (uint32_t)(g * T) * 8u, hi);
+            uint64_t b_ks = tc::sdesc64(b_lo0 + (uint32_t)(S == 1 ? g * TX : g * 2 * H) * 8u, hi);
+            for (int ks = 0; ks < nks; ++ks) {
+              const uint32_t acc = (it_u | g | ks) ? 1u : 0u;
+              uint32_t dcol = tb_u;
+              if (S == 1) {
+                uint64_t b_desc = b_ks;
+                if (K == 5) {
+  #pragma unroll
+                  for (int j = 0; j < 5; ++j) {
+                    tc::mma_tf32_elect(dcol, a_desc, b_desc, idesc, acc);
+                    b_desc += 8u;
+                    dcol += (uint32_t)a.ntpad;
+                  }
+                } else {
+                  for (int j = 0; j < K; ++j) {
+                    tc::mma_tf32_elect(dcol, a_desc, b_desc, idesc, acc);
+                    b_desc += 8u;
+                    dcol += (uint32_t)a.ntpad;
+                  }
+                }
+              } else {
+                for (int j = 0; j < K; ++j) {
+                  tc::mma_tf32_elect(dcol, a_desc, b_ks + (uint32_t)((j & 1) * H + (j >> 1)) * 8u, idesc, acc);
+                  dcol += (uint32_t)a.ntpad;
+                }
               }
-            } else {
-              for (int j = 0; j < K; ++j) {
-                const uint32_t b_lo = b_base + (uint32_t)((j & 1) * H + (j >> 1)) * 8u;
-                if (tc::elect_one()) tc::mma_tf32_lohi(dcol, a_lo, hi, b_lo, hi, idesc, acc);
-                dcol += (uint32_t)a.ntpad;
-              }
+              a_desc += 64u;
+              b_ks += 64u;
             }
           }
+        } else {
+          tc::tc_fence_after();
+          const uint32_t sbase = smem_base + (uint32_t)buf * a.buf_bytes;
+          const uint32_t a_lo0 = tc::sdesc_lo(sbase, atomA), b_lo0 = tc::sdesc_lo(sbase + a.x_off, atomX);
+          const uint32_t hi = tc::sdesc_hi(512, 1);
+          for (int g = 0; g < nsamp; ++g)
+            for (int ks = 0; ks < T / 8; ++ks) {
+              const uint32_t a_lo = a_lo0 + (uint32_t)(g * T + 8 * ks) * 8u;         // rows * 128 B >> 4
+              const uint32_t b_base = b_lo0 + (uint32_t)((S == 1 ? g * TX : g * 2 * H) + 8 * ks) * 8u;
+              uint32_t dcol = tbase;
+              const uint32_t acc = (it == 0 && g == 0 && ks == 0) ? 0u : 1u;
+              if (S == 1) {
+                uint32_t b_lo = b_base;
+                for (int j = 0; j < K; ++j) {
+                  if (tc::elect_one()) tc::mma_tf32_lohi(dcol, a_lo, hi, b_lo, hi, idesc, acc);
+                  b_lo += 8u;
+                  dcol += (uint32_t)a.ntpad;
+                }
+              } else {
+                for (int j = 0; j < K; ++j) {
+                  const uint32_t b_lo = b_base + (uint32_t)((j & 1) * H + (j >> 1)) * 8u;
+                  if (tc::elect_one()) tc::mma_tf32_lohi(dcol, a_lo, hi, b_lo, hi, idesc, acc);
+                  dcol += (uint32_t)a.ntpad;
+                }
+              }
+            }
+        }
         __syncwarp();
         if (tc::elect_one()) tc::mma_commit(&bar_free[buf]);
       }
@@ -180,6 +227,7 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
 
 // dW[co][ci][j] += sum over slices of scratch[sl][j][ci/4][co][ci%4]
 // block (32, 8): x = output float4 (coalesced 512 B per warp), y = slice group
+template <bool V2>
 __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __restrict__ scratch, float* __restrict__ dw, int Cout, int Cin,
                                                               int K, int coutp, int nslices) {
   __shared__ float4 part[8][32];
@@ -187,11 +235,24 @@ __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __res
   const int64_t slice_stride = n * 4;
   const int64_t i = (int64_t)blockIdx.x * 32 + threadIdx.x;
   float4 s = zero4();
-  if (i < n)
-    for (int sl = threadIdx.y; sl < nslices; sl += 8) {
+  if (i < n) {
+    int sl = threadIdx.y;
+    if (V2) {  // four independent 16-byte loads in flight per thread (the partials sit in L2)
+      float4 s1 = zero4();
+      const float* p = scratch + i * 4;
+      for (; sl + 24 < nslices; sl += 32) {
+        const float4 v0 = ldg4(p + (sl + 0) * slice_stride), v1 = ldg4(p + (sl + 8) * slice_stride);
+        const float4 v2 = ldg4(p + (sl + 16) * slice_stride), v3 = ldg4(p + (sl + 24) * slice_stride);
+        s.x += v0.x + v2.x; s.y += v0.y + v2.y; s.z += v0.z + v2.z; s.w += v0.w + v2.w;
+        s1.x += v1.x + v3.x; s1.y += v1.y + v3.y; s1.z += v1.z + v3.z; s1.w += v1.w + v3.w;
+      }
+      s.x += s1.x; s.y += s1.y; s.z += s1.z; s.w += s1.w;
+    }
+    for (; sl < nslices; sl += 8) {
       const float4 v = ldg4(scratch + sl * slice_stride + i * 4);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
+  }
   part[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && i < n) {
@@ -264,7 +325,8 @@ extern "C" int avc_conv_wgrad_tc(const avc_wgrad_desc* d, float* scratch, int* s
   AVC_REQUIRE(smem <= 224 * 1024, AVC_ERR_UNSUPPORTED, "avc_conv_wgrad_tc: tile does not fit shared memory");
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) {
       set_error("avc_conv_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return AVC_ERR_CUDA;
@@ -272,10 +334,14 @@ extern "C" int avc_conv_wgrad_tc(const avc_wgrad_desc* d, float* scratch, int* s
     attr_done = true;
   }
   dim3 grid(cdiv(d->Cin, WT_NT), cdiv(d->Cout, 128), a.nslices);
-  conv_wgrad_tc_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(a);
+  if (opt_tc_uniform_issue()) conv_wgrad_tc_kernel<true><<<grid, 128, smem, (cudaStream_t)stream>>>(a);
+  else conv_wgrad_tc_kernel<false><<<grid, 128, smem, (cudaStream_t)stream>>>(a);
   AVC_CHECK_LAUNCH("conv_wgrad_tc");
   const int64_t n = (int64_t)d->K * (d->Cin / 4) * a.coutp;
-  wgrad_tc_reduce_kernel<<<(int)cdiv64(n, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(scratch, d->dw, d->Cout, d->Cin, d->K, a.coutp, a.nslices);
+  if (opt_wgrad_reduce_v2())
+    wgrad_tc_reduce_kernel<true><<<(int)cdiv64(n, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(scratch, d->dw, d->Cout, d->Cin, d->K, a.coutp, a.nslices);
+  else
+    wgrad_tc_reduce_kernel<false><<<(int)cdiv64(n, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(scratch, d->dw, d->Cout, d->Cin, d->K, a.coutp, a.nslices);
   AVC_CHECK_LAUNCH("wgrad_tc_reduce");
   return AVC_OK;
 }

@@ -116,6 +116,12 @@ int64_t avc_tc_packed_floats(int co_total, int ci_total, int K);
 /* Diagnostics: device buffer of 4 int64 per CTA receiving clock64 at kernel start / main loop
  * done / epilogue done for subsequent avc_conv_block_tc launches (null disables). */
 void avc_tc_set_debug(void* dev_buffer);
+/* Runtime options (process-wide; each also has an environment default read on first use):
+ *   "tc_uniform_issue"  (AVC_TC_ISSUE=uniform|legacy)   tcgen05 issue loops on the uniform datapath
+ *   "wgrad_reduce_v2"   (AVC_WGRAD_REDUCE=v2|v1)        unrolled partial-sum reduction of conv_wgrad_tc
+ * avc_set_option returns AVC_ERR_INVALID for an unknown name; avc_get_option returns -1. */
+int avc_set_option(const char* name, int value);
+int avc_get_option(const char* name);
 /* Every re-pack of a model in one launch: a DEVICE-resident table of items (null destinations
  * are skipped); max_elems = the largest destination element count in the table. */
 typedef struct avc_pack_item {
