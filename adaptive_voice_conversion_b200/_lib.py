@@ -9,7 +9,11 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("AVC_LIB", os.path.join(_PKG, "libavc_b200.so"))
+# AVC_PDL=1 selects the programmatic-dependent-launch build of the same sources
+# (libavc_b200_pdl.so, csrc/common.cuh); the default flips only after a B200 validation run
+DEFAULT_PDL = False
+PDL = os.environ.get("AVC_PDL", "1" if DEFAULT_PDL else "0") == "1"
+LIB_PATH = os.environ.get("AVC_LIB", os.path.join(_PKG, "libavc_b200_pdl.so" if PDL else "libavc_b200.so"))
 
 PAD_REFLECT, PAD_ZERO = 0, 1
 RES_NONE, RES_SAME, RES_POOL, RES_UP = 0, 1, 2, 3

@@ -183,6 +183,7 @@ __device__ __forceinline__ void conv_epilogue(float (&acc)[8][8], const ConvArgs
 
 template <int K, int S, int TCO, int TT>
 __global__ void __launch_bounds__(256, 2) conv_block_fwd_kernel(const ConvArgs a) {
+  pdl_sync();
   using C = ConvCfg<K, S, TCO, TT>;
   extern __shared__ __align__(16) float smem[];
   float* Xs = smem;                 // [CK][XROW] planar input rows (padding resolved)
@@ -315,7 +316,8 @@ static int launch_conv(const ConvArgs& a, dim3 grid, cudaStream_t st) {
     }
     attr_done = true;
   }
-  conv_block_fwd_kernel<K, S, TCO, TT><<<grid, 256, C::SMEM_BYTES, st>>>(a);
+  void (*kern)(const ConvArgs) = conv_block_fwd_kernel<K, S, TCO, TT>;  // a macro-safe name
+  AVC_LAUNCH(kern, grid, 256, C::SMEM_BYTES, st, a);
   AVC_CHECK_LAUNCH("conv_block_fwd");
   return AVC_OK;
 }

@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc_kernel(const TcArgs a) {
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
+  pdl_sync();  // after the TMEM allocation, before the first global access (see common.cuh)
   const uint32_t tbase = tmem_slot;
   bool ok = true;
   long long tm0 = 0, tm1 = 0, tm2 = 0, dbg_acc0 = 0, dbg_acc1 = 0;
@@ -411,6 +412,7 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc_kernel(const TcArgs a) {
 // [tap][chunk 4][co 128][4 floats], TF32-rounded, zero padded: one contiguous bulk copy per stage.
 __global__ void pack_weight_tc_kernel(const float* __restrict__ w, float* __restrict__ p, int Cout, int Cin, int K, int mode,
                                       int co_total, int ci_total) {
+  pdl_sync();
   // mode FWD: conv(co', ci', j) = W[co'][ci'][j];  DGRAD: conv(co', ci', j) = W[ci'][co'][K-1-j]
   // co_total / ci_total: channel counts of the conv being packed (FWD: Cout/Cin, DGRAD: Cin/Cout)
   const int mt = (co_total + 127) / 128, nslab = (ci_total + TC_SLAB - 1) / TC_SLAB;
@@ -433,6 +435,7 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, float* __rest
 
 // All weight re-packs of a model in ONE launch: blockIdx.y walks a device-resident item table.
 __global__ void __launch_bounds__(256) pack_weights_batch_kernel(const avc_pack_item* __restrict__ items) {
+  pdl_sync();
   const avc_pack_item it = items[blockIdx.y];
   const int Cout = it.Cout, Cin = it.Cin, K = it.K;
   const int64_t nw = (int64_t)Cout * Cin * K;
@@ -490,7 +493,7 @@ extern "C" int avc_pack_conv_weights_batch(const avc_pack_item* items_dev, int n
   if (bx > 64) bx = 64;
   if (bx < 1) bx = 1;
   dim3 grid(bx, n_items);
-  pack_weights_batch_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(items_dev);
+  AVC_LAUNCH(pack_weights_batch_kernel, grid, 256, 0, (cudaStream_t)stream, items_dev);
   AVC_CHECK_LAUNCH("pack_weights_batch");
   return AVC_OK;
 }
@@ -506,7 +509,7 @@ extern "C" int avc_pack_conv_weight_tc(const float* w, float* packed, int Cout, 
   const int64_t n = avc_tc_packed_floats(co_total, ci_total, K);
   int blocks = (int)cdiv64(n, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  pack_weight_tc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, packed, Cout, Cin, K, mode, co_total, ci_total);
+  AVC_LAUNCH(pack_weight_tc_kernel, blocks, 256, 0, (cudaStream_t)stream, w, packed, Cout, Cin, K, mode, co_total, ci_total);
   AVC_CHECK_LAUNCH("pack_conv_weight_tc");
   return AVC_OK;
 }
@@ -566,8 +569,8 @@ extern "C" int avc_conv_block_tc(const avc_conv_desc* d, int* status, void* stre
     attr_smem = smem_max;
   }
   dim3 grid(cdiv(d->B, G), mtiles);
-  if (opt_tc_uniform_issue()) conv_block_tc_kernel<true><<<grid, 512, smem, (cudaStream_t)stream>>>(a);
-  else conv_block_tc_kernel<false><<<grid, 512, smem, (cudaStream_t)stream>>>(a);
+  if (opt_tc_uniform_issue()) AVC_LAUNCH(conv_block_tc_kernel<true>, grid, 512, smem, (cudaStream_t)stream, a);
+  else AVC_LAUNCH(conv_block_tc_kernel<false>, grid, 512, smem, (cudaStream_t)stream, a);
   AVC_CHECK_LAUNCH("conv_block_tc");
   return AVC_OK;
 }

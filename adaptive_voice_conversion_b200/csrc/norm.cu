@@ -44,6 +44,7 @@ __device__ __forceinline__ void load_rows(const float* cb /*sample base*/, int q
 
 template <bool SHUF>
 __global__ void __launch_bounds__(256) norm_apply_fwd_kernel(const avc_conv_desc d) {
+  pdl_sync();
   constexpr int NS = SHUF ? 2 : 1;
   const int Cn = SHUF ? d.Cout / 2 : d.Cout;
   const int Tn = SHUF ? d.Tout * 2 : d.Tout;
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(256) norm_apply_fwd_kernel(const avc_conv_desc
 
 template <bool SHUF>
 __global__ void __launch_bounds__(256) norm_bwd_kernel(const avc_conv_desc d) {
+  pdl_sync();
   constexpr int NS = SHUF ? 2 : 1;
   const int Cn = SHUF ? d.Cout / 2 : d.Cout;
   const int Tn = SHUF ? d.Tout * 2 : d.Tout;
@@ -248,6 +250,7 @@ __global__ void __launch_bounds__(256) norm_bwd_kernel(const avc_conv_desc d) {
 // norm_bwd for the common training shape (no pixel shuffle, Tout <= 128): the row of `c` and of
 // `dy` is read ONCE into registers (4 float4 each per lane) and reused by both passes.
 __global__ void __launch_bounds__(256) norm_bwd_cached_kernel(const avc_conv_desc d) {
+  pdl_sync();
   const int Cn = d.Cout, Tn = d.Tout, Cnq = Cn >> 2;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -331,6 +334,7 @@ __global__ void __launch_bounds__(256) norm_bwd_cached_kernel(const avc_conv_des
 }
 
 __global__ void __launch_bounds__(256) fold_add_kernel(const avc_fold_desc d) {
+  pdl_sync();
   const int Cq = d.C >> 2;
   const int64_t total = (int64_t)d.B * Cq * d.Tin;
   const int Lp = d.Tin + d.pad_left + d.pad_right;
@@ -374,6 +378,7 @@ __global__ void __launch_bounds__(256) fold_add_kernel(const avc_fold_desc d) {
 // grid (C/4 chunks, batch slices): block-reduce a slice of (b, t), one atomicAdd per channel
 __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ dc, int64_t bstride, float* __restrict__ dbias,
                                                         int B, int C, int T, int bps) {
+  pdl_sync();
   const int q = blockIdx.x;
   const int b0 = blockIdx.y * bps, b1 = min(B, b0 + bps);
   float4 s = zero4();
@@ -407,8 +412,8 @@ extern "C" int avc_norm_apply_fwd(const avc_conv_desc* d, void* stream) {
   const int Cn = d->shuffle ? d->Cout / 2 : d->Cout;
   const int64_t warps = (int64_t)d->B * (Cn / 4);
   const int blocks = (int)cdiv64(warps * 32, 256);
-  if (d->shuffle) norm_apply_fwd_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(*d);
-  else norm_apply_fwd_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(*d);
+  if (d->shuffle) AVC_LAUNCH(norm_apply_fwd_kernel<true>, blocks, 256, 0, (cudaStream_t)stream, *d);
+  else AVC_LAUNCH(norm_apply_fwd_kernel<false>, blocks, 256, 0, (cudaStream_t)stream, *d);
   AVC_CHECK_LAUNCH("norm_apply_fwd");
   return AVC_OK;
 }
@@ -422,9 +427,9 @@ extern "C" int avc_norm_bwd(const avc_conv_desc* d, void* stream) {
   const int Cn = d->shuffle ? d->Cout / 2 : d->Cout;
   const int64_t warps = (int64_t)d->B * (Cn / 4);
   const int blocks = (int)cdiv64(warps * 32, 256);
-  if (d->shuffle) norm_bwd_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(*d);
-  else if (d->Tout <= 128) norm_bwd_cached_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*d);
-  else norm_bwd_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(*d);
+  if (d->shuffle) AVC_LAUNCH(norm_bwd_kernel<true>, blocks, 256, 0, (cudaStream_t)stream, *d);
+  else if (d->Tout <= 128) AVC_LAUNCH(norm_bwd_cached_kernel, blocks, 256, 0, (cudaStream_t)stream, *d);
+  else AVC_LAUNCH(norm_bwd_kernel<false>, blocks, 256, 0, (cudaStream_t)stream, *d);
   AVC_CHECK_LAUNCH("norm_bwd");
   return AVC_OK;
 }
@@ -438,7 +443,7 @@ extern "C" int avc_fold_add_fwd(const avc_fold_desc* d, void* stream) {
   const int64_t total = (int64_t)d->B * (d->C / 4) * d->Tin;
   int blocks = (int)cdiv64(total, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  fold_add_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*d);
+  AVC_LAUNCH(fold_add_kernel, blocks, 256, 0, (cudaStream_t)stream, *d);
   AVC_CHECK_LAUNCH("fold_add");
   return AVC_OK;
 }
@@ -450,7 +455,7 @@ extern "C" int avc_bias_grad(const float* dc, int64_t bstride, float* dbias, int
   if (slices < 1) slices = 1;
   const int bps = cdiv(B, slices);
   dim3 grid(C / 4, cdiv(B, bps));
-  bias_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dc, bstride, dbias, B, C, T, bps);
+  AVC_LAUNCH(bias_grad_kernel, grid, 256, 0, (cudaStream_t)stream, dc, bstride, dbias, B, C, T, bps);
   AVC_CHECK_LAUNCH("bias_grad");
   return AVC_OK;
 }

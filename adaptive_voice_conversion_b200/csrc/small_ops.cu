@@ -30,6 +30,7 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ------------------------------------------------------------------ weight packing
 __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ p, int Cout, int Cin, int K, int mode) {
+  pdl_sync();
   const int64_t n = (int64_t)Cout * Cin * K;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     // i indexes the PACKED tensor so that writes are coalesced
@@ -57,6 +58,7 @@ __device__ __forceinline__ float rna_tf32(float x) {
   return __uint_as_float(r);
 }
 __global__ void pack_a4_kernel(const float* __restrict__ pl, float* __restrict__ a4, int64_t bstride, int B, int C, int T, int rnd) {
+  pdl_sync();
   const int Cq = C >> 2;
   const int64_t n = (int64_t)B * Cq * T;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -70,6 +72,7 @@ __global__ void pack_a4_kernel(const float* __restrict__ pl, float* __restrict__
   }
 }
 __global__ void unpack_a4_kernel(const float* __restrict__ a4, int64_t bstride, float* __restrict__ pl, int B, int C, int T) {
+  pdl_sync();
   const int Cq = C >> 2;
   const int64_t n = (int64_t)B * Cq * T;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -84,6 +87,7 @@ __global__ void unpack_a4_kernel(const float* __restrict__ a4, int64_t bstride, 
 
 // ------------------------------------------------------------------ mean over time
 __global__ void time_mean_fwd_kernel(const float* __restrict__ a4, int64_t bstride, float* __restrict__ out, int B, int C, int T) {
+  pdl_sync();
   const int Cq = C >> 2;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= B * Cq) return;
@@ -100,6 +104,7 @@ __global__ void time_mean_fwd_kernel(const float* __restrict__ a4, int64_t bstri
   }
 }
 __global__ void time_mean_bwd_kernel(const float* __restrict__ dout, float* __restrict__ da4, int64_t bstride, int B, int C, int T) {
+  pdl_sync();
   const int Cq = C >> 2;
   const int64_t n = (int64_t)B * Cq * T;
   const float inv = 1.f / (float)T;
@@ -116,6 +121,7 @@ __global__ void time_mean_bwd_kernel(const float* __restrict__ dout, float* __re
 // ------------------------------------------------------------------ small linear layers
 // block = 32 (n or k) x 8 (rows); tiles of 32 along the reduction dim staged in smem.
 __global__ void __launch_bounds__(256) linear_fwd_kernel(const avc_linear_desc d) {
+  pdl_sync();
   __shared__ float xs[8][33];
   __shared__ float ws[32][33];
   const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
@@ -154,6 +160,7 @@ __device__ __forceinline__ float masked_dy(const avc_linear_desc& d, int b, int 
 
 // dx[b][k] = sum_n g[b][n] W[n][k] (+ dx_add)
 __global__ void __launch_bounds__(256) linear_bwd_dx_kernel(const avc_linear_desc d) {
+  pdl_sync();
   __shared__ float gs[8][33];
   __shared__ float ws[32][33];
   const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
@@ -183,6 +190,7 @@ __global__ void __launch_bounds__(256) linear_bwd_dx_kernel(const avc_linear_des
 
 // dW[n][k] += sum_b g[b][n] x[b][k];  db[n] += sum_b g[b][n]
 __global__ void __launch_bounds__(256) linear_bwd_dw_kernel(const avc_linear_desc d) {
+  pdl_sync();
   __shared__ float gs[32][9];   // [b][n]
   __shared__ float xs[32][33];  // [b][k]
   const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
@@ -214,6 +222,7 @@ __global__ void __launch_bounds__(256) linear_bwd_dw_kernel(const avc_linear_des
 // ------------------------------------------------------------------ reparameterisation
 __global__ void reparam_fwd_kernel(const float* __restrict__ mu4, const float* __restrict__ ls4, const float* __restrict__ eps,
                                    float* __restrict__ mu, float* __restrict__ ls, float* __restrict__ z4, int B, int C, int T) {
+  pdl_sync();
   const int Cq = C >> 2;
   const int64_t n = (int64_t)B * Cq * T;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -238,6 +247,7 @@ __global__ void reparam_fwd_kernel(const float* __restrict__ mu4, const float* _
 __global__ void reparam_bwd_kernel(const float* __restrict__ dz4, const float* __restrict__ ls4, const float* __restrict__ eps,
                                    const float* __restrict__ dmu_ext, const float* __restrict__ dls_ext,
                                    float* __restrict__ dmu4, float* __restrict__ dls4, int B, int C, int T) {
+  pdl_sync();
   const int Cq = C >> 2;
   const int64_t n = (int64_t)B * Cq * T;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -280,6 +290,7 @@ __global__ void __launch_bounds__(256) vae_loss_kernel(const float* __restrict__
                                                        const float* __restrict__ mu, const float* __restrict__ ls, int64_t n_lat,
                                                        const float* __restrict__ hp, float* __restrict__ sums,
                                                        float* __restrict__ ddec, float* __restrict__ dmu, float* __restrict__ dls) {
+  pdl_sync();
   __shared__ float sh[8];
   const float lrec = hp[0], lkl = hp[1];
   const float grec = lrec / (float)n_rec, gkl = lkl / (float)n_lat;
@@ -307,6 +318,7 @@ __global__ void __launch_bounds__(256) vae_loss_kernel(const float* __restrict__
 
 // ------------------------------------------------------------------ grad norm + Adam
 __global__ void __launch_bounds__(256) sqnorm_stage1(const float* __restrict__ g, int64_t n, float* __restrict__ scratch) {
+  pdl_sync();
   __shared__ float sh[8];
   float s = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -317,6 +329,7 @@ __global__ void __launch_bounds__(256) sqnorm_stage1(const float* __restrict__ g
   if (threadIdx.x == 0) scratch[blockIdx.x] = r;
 }
 __global__ void __launch_bounds__(256) sqnorm_stage2(const float* __restrict__ scratch, int nb, float* __restrict__ out) {
+  pdl_sync();
   __shared__ float sh[8];
   float s = 0.f;
   for (int i = threadIdx.x; i < nb; i += blockDim.x) s += scratch[i];
@@ -324,12 +337,16 @@ __global__ void __launch_bounds__(256) sqnorm_stage2(const float* __restrict__ s
   if (threadIdx.x == 0) out[0] = r;
 }
 
-__global__ void step_inc_kernel(float* step) { step[0] += 1.f; }
+__global__ void step_inc_kernel(float* step) {
+  pdl_sync();
+  step[0] += 1.f;
+}
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, float* __restrict__ vmax, int64_t n,
                                                    const float* __restrict__ hp, const float* __restrict__ sqnorm,
                                                    const float* __restrict__ step) {
+  pdl_sync();
   const float gscale = hp[2], lr = hp[3], b1 = hp[4], b2 = hp[5], eps = hp[6], wd = hp[7], max_norm = hp[8];
   const bool amsgrad = hp[9] != 0.f;
   const float gnorm = gscale * sqrtf(sqnorm[0]);
@@ -410,7 +427,13 @@ extern "C" int avc_get_option(const char* name) {
 using namespace avc;
 
 extern "C" const char* avc_last_error(void) { return g_err; }
-extern "C" const char* avc_build_info(void) { return "libavc_b200 sm_100a (compute_100a) fp32-ffma + tcgen05 paths"; }
+extern "C" const char* avc_build_info(void) {
+#if AVC_PDL
+  return "libavc_b200 sm_100a (compute_100a) fp32-ffma + tcgen05 paths, pdl (programmatic dependent launch)";
+#else
+  return "libavc_b200 sm_100a (compute_100a) fp32-ffma + tcgen05 paths";
+#endif
+}
 extern "C" int64_t avc_launch_count(void) { return (int64_t)g_launches.load(); }
 
 extern "C" int avc_fill_zero(void* ptr, int64_t bytes, void* stream) {
@@ -426,20 +449,20 @@ extern "C" int avc_fill_zero(void* ptr, int64_t bytes, void* stream) {
 extern "C" int avc_pack_conv_weight(const float* w, float* packed, int Cout, int Cin, int K, int mode, void* stream) {
   AVC_REQUIRE(w && packed && Cout > 0 && Cin > 0 && K > 0, AVC_ERR_INVALID, "avc_pack_conv_weight: bad argument");
   AVC_REQUIRE(mode == AVC_PACK_FWD || mode == AVC_PACK_DGRAD, AVC_ERR_INVALID, "avc_pack_conv_weight: bad mode");
-  pack_weight_kernel<<<ew_blocks((int64_t)Cout * Cin * K), 256, 0, (cudaStream_t)stream>>>(w, packed, Cout, Cin, K, mode);
+  AVC_LAUNCH(pack_weight_kernel, ew_blocks((int64_t)Cout * Cin * K), 256, 0, (cudaStream_t)stream, w, packed, Cout, Cin, K, mode);
   AVC_CHECK_LAUNCH("pack_conv_weight");
   return AVC_OK;
 }
 
 extern "C" int avc_pack_a4(const float* planar, float* a4, int64_t a4_bstride, int B, int C, int T, int round_tf32, void* stream) {
   AVC_REQUIRE(planar && a4 && B > 0 && C > 0 && C % 4 == 0 && T > 0, AVC_ERR_INVALID, "avc_pack_a4: bad argument (C %% 4 must be 0)");
-  pack_a4_kernel<<<ew_blocks((int64_t)B * (C / 4) * T), 256, 0, (cudaStream_t)stream>>>(planar, a4, a4_bstride, B, C, T, round_tf32);
+  AVC_LAUNCH(pack_a4_kernel, ew_blocks((int64_t)B * (C / 4) * T), 256, 0, (cudaStream_t)stream, planar, a4, a4_bstride, B, C, T, round_tf32);
   AVC_CHECK_LAUNCH("pack_a4");
   return AVC_OK;
 }
 extern "C" int avc_unpack_a4(const float* a4, int64_t a4_bstride, float* planar, int B, int C, int T, void* stream) {
   AVC_REQUIRE(planar && a4 && B > 0 && C > 0 && C % 4 == 0 && T > 0, AVC_ERR_INVALID, "avc_unpack_a4: bad argument (C %% 4 must be 0)");
-  unpack_a4_kernel<<<ew_blocks((int64_t)B * (C / 4) * T), 256, 0, (cudaStream_t)stream>>>(a4, a4_bstride, planar, B, C, T);
+  AVC_LAUNCH(unpack_a4_kernel, ew_blocks((int64_t)B * (C / 4) * T), 256, 0, (cudaStream_t)stream, a4, a4_bstride, planar, B, C, T);
   AVC_CHECK_LAUNCH("unpack_a4");
   return AVC_OK;
 }
@@ -447,13 +470,13 @@ extern "C" int avc_unpack_a4(const float* a4, int64_t a4_bstride, float* planar,
 extern "C" int avc_time_mean_fwd(const float* a4, int64_t bstride, float* out, int B, int C, int T, void* stream) {
   AVC_REQUIRE(a4 && out && B > 0 && C > 0 && C % 4 == 0 && T > 0, AVC_ERR_INVALID, "avc_time_mean_fwd: bad argument");
   const int64_t warps = (int64_t)B * (C / 4);
-  time_mean_fwd_kernel<<<(int)cdiv64(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(a4, bstride, out, B, C, T);
+  AVC_LAUNCH(time_mean_fwd_kernel, (int)cdiv64(warps * 32, 256), 256, 0, (cudaStream_t)stream, a4, bstride, out, B, C, T);
   AVC_CHECK_LAUNCH("time_mean_fwd");
   return AVC_OK;
 }
 extern "C" int avc_time_mean_bwd(const float* dout, float* da4, int64_t bstride, int B, int C, int T, void* stream) {
   AVC_REQUIRE(dout && da4 && B > 0 && C > 0 && C % 4 == 0 && T > 0, AVC_ERR_INVALID, "avc_time_mean_bwd: bad argument");
-  time_mean_bwd_kernel<<<ew_blocks((int64_t)B * (C / 4) * T), 256, 0, (cudaStream_t)stream>>>(dout, da4, bstride, B, C, T);
+  AVC_LAUNCH(time_mean_bwd_kernel, ew_blocks((int64_t)B * (C / 4) * T), 256, 0, (cudaStream_t)stream, dout, da4, bstride, B, C, T);
   AVC_CHECK_LAUNCH("time_mean_bwd");
   return AVC_OK;
 }
@@ -461,7 +484,7 @@ extern "C" int avc_time_mean_bwd(const float* dout, float* da4, int64_t bstride,
 extern "C" int avc_linear_fwd(const avc_linear_desc* d, void* stream) {
   AVC_REQUIRE(d && d->x && d->w && d->out && d->B > 0 && d->N > 0 && d->K > 0, AVC_ERR_INVALID, "avc_linear_fwd: bad argument");
   dim3 grid(cdiv(d->N, 32), cdiv(d->B, 8));
-  linear_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d);
+  AVC_LAUNCH(linear_fwd_kernel, grid, 256, 0, (cudaStream_t)stream, *d);
   AVC_CHECK_LAUNCH("linear_fwd");
   return AVC_OK;
 }
@@ -470,11 +493,11 @@ extern "C" int avc_linear_bwd(const avc_linear_desc* d, void* stream) {
   AVC_REQUIRE(!d->relu || d->y_act, AVC_ERR_INVALID, "avc_linear_bwd: relu needs y_act");
   if (d->dx) {
     dim3 grid(cdiv(d->K, 32), cdiv(d->B, 8));
-    linear_bwd_dx_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d);
+    AVC_LAUNCH(linear_bwd_dx_kernel, grid, 256, 0, (cudaStream_t)stream, *d);
     AVC_CHECK_LAUNCH("linear_bwd_dx");
   }
   dim3 grid2(cdiv(d->K, 32), cdiv(d->N, 8));
-  linear_bwd_dw_kernel<<<grid2, 256, 0, (cudaStream_t)stream>>>(*d);
+  AVC_LAUNCH(linear_bwd_dw_kernel, grid2, 256, 0, (cudaStream_t)stream, *d);
   AVC_CHECK_LAUNCH("linear_bwd_dw");
   return AVC_OK;
 }
@@ -484,7 +507,7 @@ extern "C" int avc_reparam_fwd(const float* mu4, const float* ls4, const float* 
   AVC_REQUIRE(mu4 && z4 && B > 0 && C > 0 && C % 4 == 0 && T > 0, AVC_ERR_INVALID, "avc_reparam_fwd: bad argument");
   AVC_REQUIRE(!eps || ls4, AVC_ERR_INVALID, "avc_reparam_fwd: eps needs log_sigma");
   AVC_REQUIRE(!ls || ls4, AVC_ERR_INVALID, "avc_reparam_fwd: ls output needs ls4");
-  reparam_fwd_kernel<<<ew_blocks((int64_t)B * (C / 4) * T), 256, 0, (cudaStream_t)stream>>>(mu4, ls4, eps, mu, ls, z4, B, C, T);
+  AVC_LAUNCH(reparam_fwd_kernel, ew_blocks((int64_t)B * (C / 4) * T), 256, 0, (cudaStream_t)stream, mu4, ls4, eps, mu, ls, z4, B, C, T);
   AVC_CHECK_LAUNCH("reparam_fwd");
   return AVC_OK;
 }
@@ -492,7 +515,7 @@ extern "C" int avc_reparam_bwd(const float* dz4, const float* ls4, const float* 
                                float* dmu4, float* dls4, int B, int C, int T, void* stream) {
   AVC_REQUIRE(dmu4 && dls4 && B > 0 && C > 0 && C % 4 == 0 && T > 0, AVC_ERR_INVALID, "avc_reparam_bwd: bad argument");
   AVC_REQUIRE(!eps || ls4, AVC_ERR_INVALID, "avc_reparam_bwd: eps needs log_sigma");
-  reparam_bwd_kernel<<<ew_blocks((int64_t)B * (C / 4) * T), 256, 0, (cudaStream_t)stream>>>(dz4, ls4, eps, dmu_ext, dls_ext, dmu4, dls4, B, C, T);
+  AVC_LAUNCH(reparam_bwd_kernel, ew_blocks((int64_t)B * (C / 4) * T), 256, 0, (cudaStream_t)stream, dz4, ls4, eps, dmu_ext, dls_ext, dmu4, dls4, B, C, T);
   AVC_CHECK_LAUNCH("reparam_bwd");
   return AVC_OK;
 }
@@ -505,7 +528,7 @@ extern "C" int avc_vae_loss(const float* dec, const float* x, int64_t n_rec, con
     set_error("avc_vae_loss: memset: %s", cudaGetErrorString(e));
     return AVC_ERR_CUDA;
   }
-  vae_loss_kernel<<<ew_blocks(n_rec), 256, 0, (cudaStream_t)stream>>>(dec, x, n_rec, mu, ls, n_lat, hp, sums, ddec, dmu, dls);
+  AVC_LAUNCH(vae_loss_kernel, ew_blocks(n_rec), 256, 0, (cudaStream_t)stream, dec, x, n_rec, mu, ls, n_lat, hp, sums, ddec, dmu, dls);
   AVC_CHECK_LAUNCH("vae_loss");
   return AVC_OK;
 }
@@ -514,9 +537,9 @@ extern "C" int avc_sqnorm(const float* g, int64_t n, float* scratch, float* out,
   AVC_REQUIRE(g && scratch && out && n > 0, AVC_ERR_INVALID, "avc_sqnorm: bad argument");
   int nb = ew_blocks(n);
   if (nb > 1024) nb = 1024;
-  sqnorm_stage1<<<nb, 256, 0, (cudaStream_t)stream>>>(g, n, scratch);
+  AVC_LAUNCH(sqnorm_stage1, nb, 256, 0, (cudaStream_t)stream, g, n, scratch);
   AVC_CHECK_LAUNCH("sqnorm_stage1");
-  sqnorm_stage2<<<1, 256, 0, (cudaStream_t)stream>>>(scratch, nb, out);
+  AVC_LAUNCH(sqnorm_stage2, 1, 256, 0, (cudaStream_t)stream, scratch, nb, out);
   AVC_CHECK_LAUNCH("sqnorm_stage2");
   return AVC_OK;
 }
@@ -524,9 +547,9 @@ extern "C" int avc_sqnorm(const float* g, int64_t n, float* scratch, float* out,
 extern "C" int avc_adam_step(float* p, const float* g, float* m, float* v, float* vmax, int64_t n, const float* hp,
                              const float* sqnorm, float* step, void* stream) {
   AVC_REQUIRE(p && g && m && v && vmax && hp && sqnorm && step && n > 0, AVC_ERR_INVALID, "avc_adam_step: bad argument");
-  step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step);
+  AVC_LAUNCH(step_inc_kernel, 1, 1, 0, (cudaStream_t)stream, step);
   AVC_CHECK_LAUNCH("step_inc");
-  adam_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, vmax, n, hp, sqnorm, step);
+  AVC_LAUNCH(adam_kernel, ew_blocks(n), 256, 0, (cudaStream_t)stream, p, g, m, v, vmax, n, hp, sqnorm, step);
   AVC_CHECK_LAUNCH("adam");
   return AVC_OK;
 }

@@ -16,6 +16,7 @@ struct WgradArgs {
 };
 
 __global__ void __launch_bounds__(256, 2) conv_wgrad_kernel(const WgradArgs a) {
+  pdl_sync();
   __shared__ __align__(16) float As[WG_TK * WG_LD];  // dc  [t][co]
   __shared__ __align__(16) float Bs[WG_TK * WG_LD];  // x   [t][ci] (tap-shifted, reflect-padded)
   const avc_wgrad_desc& d = a.d;
@@ -106,7 +107,7 @@ extern "C" int avc_conv_wgrad(const avc_wgrad_desc* d, void* stream) {
   a.bps = cdiv(d->B, nsl);
   a.nsl = cdiv(d->B, a.bps);
   dim3 grid(cdiv(d->Cin, 128), cdiv(d->Cout, 128), d->K * a.nsl);
-  conv_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  AVC_LAUNCH(conv_wgrad_kernel, grid, 256, 0, (cudaStream_t)stream, a);
   AVC_CHECK_LAUNCH("conv_wgrad");
   return AVC_OK;
 }

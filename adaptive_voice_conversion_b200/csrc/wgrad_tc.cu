@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
+  pdl_sync();  // after the TMEM allocation, before the first global access (see common.cuh)
   const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_slot, 0);
   const uint32_t atomA = (uint32_t)a.RA * 128u, atomX = (uint32_t)a.RX * 128u;
   const uint32_t idesc = tc::make_idesc_tf32(128, a.ntpad, 1, 1);
@@ -230,6 +231,7 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
 template <bool V2>
 __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __restrict__ scratch, float* __restrict__ dw, int Cout, int Cin,
                                                               int K, int coutp, int nslices) {
+  pdl_sync();
   __shared__ float4 part[8][32];
   const int64_t n = (int64_t)K * (Cin >> 2) * coutp;
   const int64_t slice_stride = n * 4;
@@ -334,14 +336,14 @@ extern "C" int avc_conv_wgrad_tc(const avc_wgrad_desc* d, float* scratch, int* s
     attr_done = true;
   }
   dim3 grid(cdiv(d->Cin, WT_NT), cdiv(d->Cout, 128), a.nslices);
-  if (opt_tc_uniform_issue()) conv_wgrad_tc_kernel<true><<<grid, 128, smem, (cudaStream_t)stream>>>(a);
-  else conv_wgrad_tc_kernel<false><<<grid, 128, smem, (cudaStream_t)stream>>>(a);
+  if (opt_tc_uniform_issue()) AVC_LAUNCH(conv_wgrad_tc_kernel<true>, grid, 128, smem, (cudaStream_t)stream, a);
+  else AVC_LAUNCH(conv_wgrad_tc_kernel<false>, grid, 128, smem, (cudaStream_t)stream, a);
   AVC_CHECK_LAUNCH("conv_wgrad_tc");
   const int64_t n = (int64_t)d->K * (d->Cin / 4) * a.coutp;
   if (opt_wgrad_reduce_v2())
-    wgrad_tc_reduce_kernel<true><<<(int)cdiv64(n, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(scratch, d->dw, d->Cout, d->Cin, d->K, a.coutp, a.nslices);
+    AVC_LAUNCH(wgrad_tc_reduce_kernel<true>, (int)cdiv64(n, 32), dim3(32, 8), 0, (cudaStream_t)stream, scratch, d->dw, d->Cout, d->Cin, d->K, a.coutp, a.nslices);
   else
-    wgrad_tc_reduce_kernel<false><<<(int)cdiv64(n, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(scratch, d->dw, d->Cout, d->Cin, d->K, a.coutp, a.nslices);
+    AVC_LAUNCH(wgrad_tc_reduce_kernel<false>, (int)cdiv64(n, 32), dim3(32, 8), 0, (cudaStream_t)stream, scratch, d->dw, d->Cout, d->Cin, d->K, a.coutp, a.nslices);
   AVC_CHECK_LAUNCH("wgrad_tc_reduce");
   return AVC_OK;
 }
