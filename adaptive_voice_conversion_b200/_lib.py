@@ -12,6 +12,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 # AVC_PDL=1 selects the programmatic-dependent-launch build of the same sources
 # (libavc_b200_pdl.so, csrc/common.cuh); the default flips only after a B200 validation run
 DEFAULT_PDL = False
+DEFAULT_FUSED_DENSE = False  # engine.py: fused speaker dense stack / batched AdaIN affine layers
 PDL = os.environ.get("AVC_PDL", "1" if DEFAULT_PDL else "0") == "1"
 LIB_PATH = os.environ.get("AVC_LIB", os.path.join(_PKG, "libavc_b200_pdl.so" if PDL else "libavc_b200.so"))
 
@@ -80,6 +81,26 @@ class LinearDesc(C.Structure):
     ]
 
 
+class DenseStackDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("C", C.c_int32), ("c_out", C.c_int32), ("n_blocks", C.c_int32),
+        ("params", _fp), ("x", _fp), ("save", _fp), ("out", _fp), ("dout", _fp), ("gsave", _fp), ("dx", _fp),
+    ]
+
+
+LINEAR_BATCH_MAX = 16
+
+
+class LinearBatchDesc(C.Structure):
+    _fields_ = [
+        ("L", C.c_int32), ("B", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("params", _fp), ("grads", _fp),
+        ("x", _fp), ("x_off", C.c_int64 * LINEAR_BATCH_MAX), ("x_bstride", C.c_int64),
+        ("y", _fp), ("out", _fp), ("y_off", C.c_int64 * LINEAR_BATCH_MAX), ("y_bstride", C.c_int64),
+        ("part", _fp), ("dx_add", _fp), ("dx", _fp),
+    ]
+
+
 # name -> (restype, argtypes); the single source of truth for tests/test_cabi_symbols.py
 _i, _i64, _p = C.c_int, C.c_int64, C.c_void_p
 PROTOTYPES = {
@@ -105,6 +126,11 @@ PROTOTYPES = {
     "avc_time_mean_bwd": (_i, [_p, _p, _i64, _i, _i, _i, _p]),
     "avc_linear_fwd": (_i, [C.POINTER(LinearDesc), _p]),
     "avc_linear_bwd": (_i, [C.POINTER(LinearDesc), _p]),
+    "avc_dense_stack_fwd": (_i, [C.POINTER(DenseStackDesc), _p]),
+    "avc_dense_stack_bwd": (_i, [C.POINTER(DenseStackDesc), _p]),
+    "avc_linear_batch_fwd": (_i, [C.POINTER(LinearBatchDesc), _p]),
+    "avc_linear_batch_dx": (_i, [C.POINTER(LinearBatchDesc), _p]),
+    "avc_linear_batch_dw": (_i, [C.POINTER(LinearBatchDesc), _p]),
     "avc_reparam_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "avc_reparam_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "avc_vae_loss": (_i, [_p, _p, _i64, _p, _p, _i64, _p, _p, _p, _p, _p, _p]),

@@ -76,6 +76,10 @@ class Engine:
             raise L.AvcError("AVC_PRECISION must be 'tf32' or 'fp32'")
         self.tc_status = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self._packed_key = None
+        # opt-in: the speaker dense stack as one kernel per direction and the 12 AdaIN affine layers
+        # as one launch each (csrc/dense_fused.cu); off = one launch per nn.Linear
+        self.fused_dense = os.environ.get("AVC_FUSED_DENSE", "1" if L.DEFAULT_FUSED_DENSE else "0") == "1"
+        self._ptr_tables: Dict[tuple, tuple] = {}
         se, ce, de = config["SpeakerEncoder"], config["ContentEncoder"], config["Decoder"]
         for c in (se, ce):
             if c.get("act", "relu") != "relu" or c.get("dropout_rate", 0) != 0:
@@ -112,6 +116,15 @@ class Engine:
         t = self.empty(*shape)
         self._ck(self.lib.avc_fill_zero(t.data_ptr(), t.numel() * 4, self.stream), "fill_zero")
         return t
+
+    def _ptr_table(self, key, tensors) -> torch.Tensor:
+        """Device-resident table of the tensors' addresses (int64), cached until one of them moves."""
+        ptrs = tuple(t.data_ptr() for t in tensors)
+        hit = self._ptr_tables.get(key)
+        if hit is None or hit[0] != ptrs:
+            hit = (ptrs, torch.tensor(ptrs, dtype=torch.int64).to(self.dev))
+            self._ptr_tables[key] = hit
+        return hit[1]
 
     def pack_a4(self, planar: torch.Tensor, dst: A4):
         B, Cc, T = planar.shape
@@ -466,9 +479,23 @@ class Engine:
         B = out.B
         pooled = self.empty(B, out.C)
         self._ck(self.lib.avc_time_mean_fwd(out.ptr, out.bstride, pooled.data_ptr(), B, out.C, out.T, self.stream), "time_mean_fwd")
+        nd = c["n_dense_blocks"]
+        if self.fused_dense and out.C == 128 and c["c_out"] == 128:
+            names = [f"{enc}.first_dense_layers.{l}" for l in range(nd)] + [f"{enc}.second_dense_layers.{l}" for l in range(nd)]
+            names.append(f"{enc}.output_layer")
+            tab = self._ptr_table(("dense", enc), [P[n + sfx] for n in names for sfx in (".weight", ".bias")])
+            save = self.empty(3 * nd + 1, B, 128) if train else None
+            emb = self.empty(B, 128)
+            d = L.DenseStackDesc()
+            d.B, d.C, d.c_out, d.n_blocks = B, 128, 128, nd
+            d.params, d.x, d.save, d.out = tab.data_ptr(), pooled.data_ptr(), _ptr(save), emb.data_ptr()
+            self._ck(self.lib.avc_dense_stack_fwd(C.byref(d), self.stream), "dense_stack_fwd")
+            if train:
+                ctx.update(dense_fused=dict(save=save, tab=tab, names=names, pooled=pooled), last=out)
+            return emb, ctx
         h = pooled
         dense = []
-        for l in range(c["n_dense_blocks"]):
+        for l in range(nd):
             y, r1 = self.linear(P, f"{enc}.first_dense_layers.{l}", h, relu=True, train=train)
             h, r2 = self.linear(P, f"{enc}.second_dense_layers.{l}", y, relu=True, res=h, train=train)
             dense.append((r1, r2))
@@ -479,11 +506,32 @@ class Engine:
 
     def speaker_bwd(self, P, G, ctx, demb: torch.Tensor):
         c = self.cfg["SpeakerEncoder"]
-        dh = self.linear_bwd(P, G, ctx["out_rec"], demb)
-        for r1, r2 in reversed(ctx["dense"]):
-            dy = self.linear_bwd(P, G, r2, dh)                 # through second layer (+ReLU mask)
-            dh = self.linear_bwd(P, G, r1, dy, dx_add=dh)       # through first layer, + identity branch
         last = ctx["last"]
+        if "dense_fused" in ctx:
+            f = ctx["dense_fused"]
+            nd, B = c["n_dense_blocks"], last.B
+            gsave, dh = self.empty(2 * nd + 1, B, 128), self.empty(B, 128)
+            demb = demb.contiguous()
+            d = L.DenseStackDesc()
+            d.B, d.C, d.c_out, d.n_blocks = B, 128, 128, nd
+            d.params, d.save, d.dout = f["tab"].data_ptr(), f["save"].data_ptr(), demb.data_ptr()
+            d.gsave, d.dx = gsave.data_ptr(), dh.data_ptr()
+            self._ck(self.lib.avc_dense_stack_bwd(C.byref(d), self.stream), "dense_stack_bwd")
+            # weight gradients of the 2n+1 layers in one launch: (gsave plane, save plane) per layer
+            gtab = self._ptr_table(("dense_grads", "speaker_encoder"), [G[n + sfx] for n in f["names"] for sfx in (".weight", ".bias")])
+            plane = B * 128
+            slots = [(l, l) for l in range(nd)] + [(nd + l, nd + 1 + l) for l in range(nd)] + [(2 * nd, nd)]
+            bd = L.LinearBatchDesc()
+            bd.L, bd.B, bd.N, bd.K = len(slots), B, 128, 128
+            bd.grads, bd.x, bd.x_bstride, bd.y, bd.y_bstride = gtab.data_ptr(), f["save"].data_ptr(), 128, gsave.data_ptr(), 128
+            for i, (gs, xs) in enumerate(slots):
+                bd.y_off[i], bd.x_off[i] = gs * plane, xs * plane
+            self._ck(self.lib.avc_linear_batch_dw(C.byref(bd), self.stream), "linear_batch_dw[dense]")
+        else:
+            dh = self.linear_bwd(P, G, ctx["out_rec"], demb)
+            for r1, r2 in reversed(ctx["dense"]):
+                dy = self.linear_bwd(P, G, r2, dh)                 # through second layer (+ReLU mask)
+                dh = self.linear_bwd(P, G, r1, dy, dx_add=dh)       # through first layer, + identity branch
         dout = A4.empty(last.B, last.C, last.T, self.dev)
         self._ck(self.lib.avc_time_mean_bwd(dh.data_ptr(), dout.ptr, dout.bstride, last.B, last.C, last.T, self.stream), "time_mean_bwd")
         self._enc_bwd(P, G, "speaker_encoder", c, ctx, dout)
@@ -571,9 +619,23 @@ class Engine:
         ch2 = 2 * c["c_h"]
         conds = self.empty(z4.B, 2 * nblk, ch2)
         aff = []
-        for i in range(2 * nblk):
-            _, r = self.linear(P, f"{dn}.conv_affine_layers.{i}", emb, out=conds[:, i], train=train)
-            aff.append(r)
+        naff = 2 * nblk
+        fused_aff = self.fused_dense and naff <= L.LINEAR_BATCH_MAX and emb.is_contiguous()
+        if fused_aff:
+            anames = [f"{dn}.conv_affine_layers.{i}" for i in range(naff)]
+            tab = self._ptr_table(("affine", dn), [P[n + sfx] for n in anames for sfx in (".weight", ".bias")])
+            bd = L.LinearBatchDesc()
+            bd.L, bd.B, bd.N, bd.K = naff, z4.B, ch2, emb.shape[1]
+            bd.params, bd.x, bd.x_bstride = tab.data_ptr(), emb.data_ptr(), emb.stride(0)
+            bd.out, bd.y_bstride = conds.data_ptr(), naff * ch2
+            for i in range(naff):
+                bd.x_off[i], bd.y_off[i] = 0, i * ch2
+            self._ck(self.lib.avc_linear_batch_fwd(C.byref(bd), self.stream), "linear_batch_fwd[affine]")
+            aff = dict(tab=tab, names=anames)
+        else:
+            for i in range(naff):
+                _, r = self.linear(P, f"{dn}.conv_affine_layers.{i}", emb, out=conds[:, i], train=train)
+                aff.append(r)
         blocks = []
         for l, up in enumerate(c["upsample"][:nblk]):
             y, r1 = self.conv(P, f"{dn}.first_conv_layers.{l}", out, norm=True, cond=conds[:, 2 * l], relu=True, train=train)
@@ -598,6 +660,23 @@ class Engine:
             dout = self.conv_bwd(P, G, r1, dy1, dres=dout, dres_mode=L.RES_UP if up > 1 else L.RES_SAME, dcond=dconds[:, 2 * l])
         dz4 = self.conv_bwd(P, G, ctx["in_rec"], dout, need_dx=need_dz)
         demb = None
-        for i, r in enumerate(ctx["aff"]):
-            demb = self.linear_bwd(P, G, r, dconds[:, i], dx_add=demb)
+        aff = ctx["aff"]
+        if isinstance(aff, dict):   # the 2n affine layers in three launches
+            emb = ctx["emb"]
+            naff, B, ch2, K = len(aff["names"]), emb.shape[0], dconds.shape[2], emb.shape[1]
+            gtab = self._ptr_table(("affine_grads", "decoder"), [G[n + sfx] for n in aff["names"] for sfx in (".weight", ".bias")])
+            part, demb = self.empty(naff, B, K), self.empty(B, K)
+            bd = L.LinearBatchDesc()
+            bd.L, bd.B, bd.N, bd.K = naff, B, ch2, K
+            bd.params, bd.grads = aff["tab"].data_ptr(), gtab.data_ptr()
+            bd.x, bd.x_bstride = emb.data_ptr(), emb.stride(0)
+            bd.y, bd.y_bstride = dconds.data_ptr(), naff * ch2
+            for i in range(naff):
+                bd.x_off[i], bd.y_off[i] = 0, i * ch2
+            bd.part, bd.dx = part.data_ptr(), demb.data_ptr()
+            self._ck(self.lib.avc_linear_batch_dx(C.byref(bd), self.stream), "linear_batch_dx[affine]")
+            self._ck(self.lib.avc_linear_batch_dw(C.byref(bd), self.stream), "linear_batch_dw[affine]")
+        else:
+            for i, r in enumerate(aff):
+                demb = self.linear_bwd(P, G, r, dconds[:, i], dx_add=demb)
         return dz4, demb

@@ -214,6 +214,51 @@ typedef struct avc_linear_desc {
 int avc_linear_fwd(const avc_linear_desc* d, void* stream);
 int avc_linear_bwd(const avc_linear_desc* d, void* stream); /* mask = (y_act > 0) when relu */
 
+/* The SpeakerEncoder tail as one kernel per direction (model.py:252-263 dense_blocks, :273-276
+ * output_layer): n_blocks x { y = relu(W1 h + b1); a = relu(W2 y + b2); h = a + h }, out = Wo h + bo.
+ * Built for C = c_out = 128 (AVC_ERR_UNSUPPORTED otherwise: use avc_linear_fwd/bwd per layer).
+ * params: DEVICE table of 4*n_blocks+2 pointers [W1_l, b1_l]* [W2_l, b2_l]* Wo bo (nn.Linear layouts).
+ * save  : [3*n_blocks+1][B][C] planes h_0..h_n | y_0.. | a_0.. (null at inference).
+ * gsave : [2*n_blocks+1][B][C] planes g1_0.. | g2_0.. | dout: the ReLU-masked upstream gradient of
+ *         every linear layer = left operand of its weight gradient (avc_linear_batch_dw). */
+typedef struct avc_dense_stack_desc {
+  int32_t B, C, c_out, n_blocks;
+  const float* const* params;
+  const float* x; /* [B][C] */
+  float* save;
+  float* out;        /* [B][c_out] */
+  const float* dout; /* [B][c_out] (backward) */
+  float* gsave;
+  float* dx; /* [B][C] */
+} avc_dense_stack_desc;
+int avc_dense_stack_fwd(const avc_dense_stack_desc* d, void* stream);
+int avc_dense_stack_bwd(const avc_dense_stack_desc* d, void* stream);
+
+/* L same-shape nn.Linear layers per launch (the 12 AdaIN affine layers model.py:342-343; the weight
+ * gradients of the dense stack).  Layer l reads x + x_off[l] ([B][K], rows x_bstride apart) and
+ * reads/writes the [B][N] tensor at y_off[l] (rows y_bstride apart): `out` in _fwd, the upstream
+ * gradient `y` in _dx/_dw.  params / grads: DEVICE tables [W_l, b_l]* / [dW_l, db_l]* (accumulated).
+ * _dx: dx[B][K] = sum_l y_l W_l (+ dx_add) through the scratch part[L][B][K]. */
+#define AVC_LINEAR_BATCH_MAX 16
+typedef struct avc_linear_batch_desc {
+  int32_t L, B, N, K;
+  const float* const* params;
+  float* const* grads;
+  const float* x;
+  int64_t x_off[AVC_LINEAR_BATCH_MAX];
+  int64_t x_bstride;
+  const float* y;
+  float* out;
+  int64_t y_off[AVC_LINEAR_BATCH_MAX];
+  int64_t y_bstride;
+  float* part;
+  const float* dx_add;
+  float* dx;
+} avc_linear_batch_desc;
+int avc_linear_batch_fwd(const avc_linear_batch_desc* d, void* stream);
+int avc_linear_batch_dx(const avc_linear_batch_desc* d, void* stream);
+int avc_linear_batch_dw(const avc_linear_batch_desc* d, void* stream);
+
 /* VAE reparameterisation (model.py:383-384) fused with the A4->planar conversion of the
  * two heads: z = mu + exp(log_sigma/2)*eps (eps null: z = mu, the inference path :389-390). */
 int avc_reparam_fwd(const float* mu4, const float* ls4, const float* eps /*planar or null*/,
