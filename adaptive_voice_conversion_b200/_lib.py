@@ -10,9 +10,12 @@ import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 # AVC_PDL=1 selects the programmatic-dependent-launch build of the same sources
-# (libavc_b200_pdl.so, csrc/common.cuh); the default flips only after a B200 validation run
+# (libavc_b200_pdl.so, csrc/common.cuh).  Validated on the B200 (all parity tests green) but it
+# bought nothing inside the CUDA-graph step (42 068 vs 42 513 seg/s), so it stays opt-in.
 DEFAULT_PDL = False
-DEFAULT_FUSED_DENSE = False  # engine.py: fused speaker dense stack / batched AdaIN affine layers
+# engine.py: fused speaker dense stack / batched AdaIN affine layers (csrc/dense_fused.cu); ON since
+# the B200 validation run (42 513 -> 45 462 seg/s); AVC_FUSED_DENSE=0 = one launch per nn.Linear
+DEFAULT_FUSED_DENSE = True
 PDL = os.environ.get("AVC_PDL", "1" if DEFAULT_PDL else "0") == "1"
 LIB_PATH = os.environ.get("AVC_LIB", os.path.join(_PKG, "libavc_b200_pdl.so" if PDL else "libavc_b200.so"))
 

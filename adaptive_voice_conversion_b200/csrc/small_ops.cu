@@ -7,12 +7,14 @@
 
 #include "common.cuh"
 
-// defaults of the runtime options (avc_set_option); flipped only after a B200 validation run
+// defaults of the runtime options (avc_set_option).  Both are ON since the B200 validation run of
+// tools/validate_opts.sh (profiles/r1_opts_validation.md): 56 tcgen05 / model parity tests green,
+// 39 856 -> 42 513 seg/s.  AVC_TC_ISSUE=legacy / AVC_WGRAD_REDUCE=v1 select the round-1 kernels.
 #ifndef AVC_DEFAULT_TC_UNIFORM_ISSUE
-#define AVC_DEFAULT_TC_UNIFORM_ISSUE 0
+#define AVC_DEFAULT_TC_UNIFORM_ISSUE 1
 #endif
 #ifndef AVC_DEFAULT_WGRAD_REDUCE_V2
-#define AVC_DEFAULT_WGRAD_REDUCE_V2 0
+#define AVC_DEFAULT_WGRAD_REDUCE_V2 1
 #endif
 
 namespace avc {

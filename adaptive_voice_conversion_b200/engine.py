@@ -126,6 +126,28 @@ class Engine:
             self._ptr_tables[key] = hit
         return hit[1]
 
+    def _dense_names(self, enc="speaker_encoder"):
+        nd = self.cfg["SpeakerEncoder"]["n_dense_blocks"]
+        return ([f"{enc}.first_dense_layers.{l}" for l in range(nd)] + [f"{enc}.second_dense_layers.{l}" for l in range(nd)]
+                + [f"{enc}.output_layer"])
+
+    def _affine_names(self, dn="decoder"):
+        return [f"{dn}.conv_affine_layers.{i}" for i in range(2 * self.cfg["Decoder"]["n_conv_blocks"])]
+
+    def _param_table(self, kind: str, names, D: Dict[str, torch.Tensor]) -> torch.Tensor:
+        return self._ptr_table((kind, names[0]), [D[n + sfx] for n in names for sfx in (".weight", ".bias")])
+
+    def prepare_tables(self, P, G=None):
+        """Build the device pointer tables of the fused dense paths NOW (a host-to-device copy):
+        they must exist before a CUDA-graph capture, which cannot contain that copy."""
+        if not self.fused_dense:
+            return
+        for names in (self._dense_names(), self._affine_names()):
+            if all(n + ".weight" in P for n in names):
+                self._param_table("params", names, P)
+                if G is not None:
+                    self._param_table("grads", names, G)
+
     def pack_a4(self, planar: torch.Tensor, dst: A4):
         B, Cc, T = planar.shape
         assert planar.is_contiguous() and planar.dtype == torch.float32
@@ -481,9 +503,8 @@ class Engine:
         self._ck(self.lib.avc_time_mean_fwd(out.ptr, out.bstride, pooled.data_ptr(), B, out.C, out.T, self.stream), "time_mean_fwd")
         nd = c["n_dense_blocks"]
         if self.fused_dense and out.C == 128 and c["c_out"] == 128:
-            names = [f"{enc}.first_dense_layers.{l}" for l in range(nd)] + [f"{enc}.second_dense_layers.{l}" for l in range(nd)]
-            names.append(f"{enc}.output_layer")
-            tab = self._ptr_table(("dense", enc), [P[n + sfx] for n in names for sfx in (".weight", ".bias")])
+            names = self._dense_names(enc)
+            tab = self._param_table("params", names, P)
             save = self.empty(3 * nd + 1, B, 128) if train else None
             emb = self.empty(B, 128)
             d = L.DenseStackDesc()
@@ -518,7 +539,7 @@ class Engine:
             d.gsave, d.dx = gsave.data_ptr(), dh.data_ptr()
             self._ck(self.lib.avc_dense_stack_bwd(C.byref(d), self.stream), "dense_stack_bwd")
             # weight gradients of the 2n+1 layers in one launch: (gsave plane, save plane) per layer
-            gtab = self._ptr_table(("dense_grads", "speaker_encoder"), [G[n + sfx] for n in f["names"] for sfx in (".weight", ".bias")])
+            gtab = self._param_table("grads", f["names"], G)
             plane = B * 128
             slots = [(l, l) for l in range(nd)] + [(nd + l, nd + 1 + l) for l in range(nd)] + [(2 * nd, nd)]
             bd = L.LinearBatchDesc()
@@ -622,8 +643,8 @@ class Engine:
         naff = 2 * nblk
         fused_aff = self.fused_dense and naff <= L.LINEAR_BATCH_MAX and emb.is_contiguous()
         if fused_aff:
-            anames = [f"{dn}.conv_affine_layers.{i}" for i in range(naff)]
-            tab = self._ptr_table(("affine", dn), [P[n + sfx] for n in anames for sfx in (".weight", ".bias")])
+            anames = self._affine_names(dn)
+            tab = self._param_table("params", anames, P)
             bd = L.LinearBatchDesc()
             bd.L, bd.B, bd.N, bd.K = naff, z4.B, ch2, emb.shape[1]
             bd.params, bd.x, bd.x_bstride = tab.data_ptr(), emb.data_ptr(), emb.stride(0)
@@ -664,7 +685,7 @@ class Engine:
         if isinstance(aff, dict):   # the 2n affine layers in three launches
             emb = ctx["emb"]
             naff, B, ch2, K = len(aff["names"]), emb.shape[0], dconds.shape[2], emb.shape[1]
-            gtab = self._ptr_table(("affine_grads", "decoder"), [G[n + sfx] for n in aff["names"] for sfx in (".weight", ".bias")])
+            gtab = self._param_table("grads", aff["names"], G)
             part, demb = self.empty(naff, B, K), self.empty(B, K)
             bd = L.LinearBatchDesc()
             bd.L, bd.B, bd.N, bd.K = naff, B, ch2, K

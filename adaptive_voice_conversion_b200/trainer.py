@@ -44,6 +44,7 @@ class FusedTrainer:
         self._static = None
         self.launches_per_step = 0
         self.eng.pack_weights(self.P, need_dgrad=True)
+        self.eng.prepare_tables(self.P, self.G)   # before any CUDA-graph capture
         self._lambda_kl = None
         opt.sync_hparams(lambda_rec=float(config["lambda"]["lambda_rec"]), lambda_kl=float(config["lambda"]["lambda_kl"]))
 
@@ -110,6 +111,7 @@ class FusedTrainer:
         """Capture the step for x_example's shape into CUDA graphs.  Runs `warmup` real
         (eager) steps first -- they DO update the parameters."""
         lam = self._lambda_kl if self._lambda_kl is not None else float(self.cfg["lambda"]["lambda_kl"])
+        self.eng.prepare_tables(self.P, self.G)
         self._static = x_example.contiguous().clone()
         for _ in range(warmup):
             self.step(self._static, lam)

@@ -7,11 +7,7 @@ import torch
 import oracle.ae_oracle as orc
 from test_gpu_kernels import relerr, rnd
 
-import os
-
-# not yet run on a B200: opt in with AVC_TEST_EXPERIMENTAL=1 (tools/validate_opts.sh does)
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("AVC_TEST_EXPERIMENTAL") != "1", reason="experimental path: set AVC_TEST_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 TOL = 2e-4
 
 
