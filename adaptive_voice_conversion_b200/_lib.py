@@ -16,6 +16,9 @@ DEFAULT_PDL = False
 # engine.py: fused speaker dense stack / batched AdaIN affine layers (csrc/dense_fused.cu); ON since
 # the B200 validation run (42 513 -> 45 462 seg/s); AVC_FUSED_DENSE=0 = one launch per nn.Linear
 DEFAULT_FUSED_DENSE = True
+# engine.py: conv weight gradients accumulated in place with vector atomics + ONE flush launch per
+# backward pass (csrc/wgrad_tc.cu, ATOMIC); not yet run on a B200 -> opt in with AVC_WGRAD_ACC=1
+DEFAULT_WGRAD_ACC = False
 PDL = os.environ.get("AVC_PDL", "1" if DEFAULT_PDL else "0") == "1"
 LIB_PATH = os.environ.get("AVC_LIB", os.path.join(_PKG, "libavc_b200_pdl.so" if PDL else "libavc_b200.so"))
 
@@ -84,6 +87,10 @@ class LinearDesc(C.Structure):
     ]
 
 
+class WgradAccItem(C.Structure):
+    _fields_ = [("acc", _fp), ("dw", _fp), ("Cout", C.c_int32), ("Cin", C.c_int32), ("K", C.c_int32), ("reserved", C.c_int32)]
+
+
 class DenseStackDesc(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("C", C.c_int32), ("c_out", C.c_int32), ("n_blocks", C.c_int32),
@@ -120,6 +127,9 @@ PROTOTYPES = {
     "avc_conv_wgrad": (_i, [C.POINTER(WgradDesc), _p]),
     "avc_wgrad_tc_scratch_floats": (_i64, [C.POINTER(WgradDesc)]),
     "avc_conv_wgrad_tc": (_i, [C.POINTER(WgradDesc), _p, _p, _p]),
+    "avc_wgrad_acc_floats": (_i64, [_i, _i, _i]),
+    "avc_conv_wgrad_tc_acc": (_i, [C.POINTER(WgradDesc), _p, _p, _p]),
+    "avc_wgrad_acc_flush": (_i, [_p, _i, _i64, _p]),
     "avc_fold_add_fwd": (_i, [C.POINTER(FoldDesc), _p]),
     "avc_pack_conv_weight": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "avc_pack_a4": (_i, [_p, _p, _i64, _i, _i, _i, _i, _p]),

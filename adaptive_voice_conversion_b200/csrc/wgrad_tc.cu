@@ -47,8 +47,12 @@ __device__ __forceinline__ uint32_t mn_unit_off(int q, int row, uint32_t atom_by
   return (uint32_t)(q >> 3) * atom_bytes + (uint32_t)row * 128u + (uint32_t)((((q & 7) >> 1) ^ (row & 3)) << 5) + (uint32_t)((q & 1) << 4);
 }
 
-// UI (uniform issue): see conv_tc.cu; UI = false is the round-1 issue loop
-template <bool UI>
+// UI (uniform issue): see conv_tc.cu; UI = false is the round-1 issue loop.
+// ATOMIC: the epilogue adds the CTA's partial straight into ONE accumulation buffer per layer
+// ([tap][ci/4][co][4], vector red.global.add.v4.f32) instead of writing a per-slice partial: no
+// scratch round trip and no per-layer reduction launch (avc_wgrad_acc_flush unpacks every layer at
+// the end of the backward pass); the price is a run-to-run summation order.
+template <bool UI, bool ATOMIC>
 __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_free[2], bar_done;
@@ -209,14 +213,20 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
     const int co = co0 + tid;
     const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
     for (int j = 0; j < K; ++j) {
-      float* sbase = a.scratch + (((size_t)sl * K + j) * (size_t)(d.Cin >> 2)) * (size_t)a.coutp * 4;
+      float* sbase = a.scratch + (((size_t)(ATOMIC ? 0 : sl) * K + j) * (size_t)(d.Cin >> 2)) * (size_t)a.coutp * 4;
       for (int c0 = 0; c0 < a.ntpad; c0 += 16) {
         float v[16];
         tc::tmem_ld16(lane_addr + (uint32_t)(j * a.ntpad + c0), v);
 #pragma unroll
         for (int i4 = 0; i4 < 16; i4 += 4) {
           const int ci = ci0 + c0 + i4;
-          if (ci < d.Cin) st4(sbase + ((size_t)(ci >> 2) * a.coutp + co) * 4, make_float4(v[i4], v[i4 + 1], v[i4 + 2], v[i4 + 3]));
+          if (ci < d.Cin) {
+            float* p = sbase + ((size_t)(ci >> 2) * a.coutp + co) * 4;
+            if constexpr (ATOMIC)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[i4]), "f"(v[i4 + 1]), "f"(v[i4 + 2]), "f"(v[i4 + 3]) : "memory");
+            else
+              st4(p, make_float4(v[i4], v[i4 + 1], v[i4 + 2], v[i4 + 3]));
+          }
         }
       }
     }
@@ -270,6 +280,27 @@ __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __res
   }
 }
 
+// dW[co][ci][j] += acc[j][ci/4][co][ci%4]; acc = 0.   grid.y = layer (device item table), grid.x
+// covers the largest layer (smaller layers exit early)
+__global__ void __launch_bounds__(256) wgrad_acc_flush_kernel(const avc_wgrad_acc_item* __restrict__ items) {
+  pdl_sync();
+  const avc_wgrad_acc_item it = items[blockIdx.y];
+  const int coutp = cdiv(it.Cout, 128) * 128;
+  const int64_t n = (int64_t)it.K * (it.Cin >> 2) * coutp;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4* a4 = reinterpret_cast<float4*>(it.acc) + i;
+  const float4 s = *a4;
+  *a4 = zero4();
+  const int co = (int)(i % coutp);
+  if (co < it.Cout) {
+    const int64_t r = i / coutp;
+    const int c4 = (int)(r % (it.Cin >> 2)), j = (int)(r / (it.Cin >> 2));
+    float* o = it.dw + ((int64_t)co * it.Cin + c4 * 4) * it.K + j;
+    o[0] += s.x; o[it.K] += s.y; o[2 * it.K] += s.z; o[3 * it.K] += s.w;
+  }
+}
+
 static int wgrad_tc_plan(const avc_wgrad_desc* d, WgTcArgs& a) {
   const int T = d->Tout, K = d->K;
   a.d = *d;
@@ -315,35 +346,60 @@ extern "C" int64_t avc_wgrad_tc_scratch_floats(const avc_wgrad_desc* d) {
   return (int64_t)a.nslices * d->K * d->Cin * a.coutp;
 }
 
-extern "C" int avc_conv_wgrad_tc(const avc_wgrad_desc* d, float* scratch, int* status, void* stream) {
-  AVC_REQUIRE(d && d->x && d->dc && d->dw && scratch && status, AVC_ERR_INVALID, "avc_conv_wgrad_tc: null argument");
-  AVC_REQUIRE(d->B > 0 && d->Cin > 0 && d->Cout > 0 && d->Tin > 0 && d->Tout > 0, AVC_ERR_INVALID, "avc_conv_wgrad_tc: bad shape");
-  AVC_REQUIRE(wgrad_tc_supported(d), AVC_ERR_UNSUPPORTED, "avc_conv_wgrad_tc: needs stride 1 (Tout <= 128) or 2 (Tout <= 64), Tout %% 8 == 0, K <= 8");
+static int wgrad_tc_launch(const avc_wgrad_desc* d, float* scratch, int* status, void* stream, bool accumulate, const char* who) {
+  AVC_REQUIRE(d && d->x && d->dc && scratch && status && (accumulate || d->dw), AVC_ERR_INVALID, "%s: null argument", who);
+  AVC_REQUIRE(d->B > 0 && d->Cin > 0 && d->Cout > 0 && d->Tin > 0 && d->Tout > 0, AVC_ERR_INVALID, "%s: bad shape", who);
+  AVC_REQUIRE(wgrad_tc_supported(d), AVC_ERR_UNSUPPORTED, "%s: needs stride 1 (Tout <= 128) or 2 (Tout <= 64), Tout %% 8 == 0, K <= 8", who);
   WgTcArgs a;
   wgrad_tc_plan(d, a);
   a.scratch = scratch;
   a.status = status;
   const int smem = 2 * (int)a.buf_bytes;
-  AVC_REQUIRE(smem <= 224 * 1024, AVC_ERR_UNSUPPORTED, "avc_conv_wgrad_tc: tile does not fit shared memory");
+  AVC_REQUIRE(smem <= 224 * 1024, AVC_ERR_UNSUPPORTED, "%s: tile does not fit shared memory", who);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
     if (e != cudaSuccess) {
-      set_error("avc_conv_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      set_error("%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e));
       return AVC_ERR_CUDA;
     }
     attr_done = true;
   }
   dim3 grid(cdiv(d->Cin, WT_NT), cdiv(d->Cout, 128), a.nslices);
-  if (opt_tc_uniform_issue()) AVC_LAUNCH(conv_wgrad_tc_kernel<true>, grid, 128, smem, (cudaStream_t)stream, a);
-  else AVC_LAUNCH(conv_wgrad_tc_kernel<false>, grid, 128, smem, (cudaStream_t)stream, a);
-  AVC_CHECK_LAUNCH("conv_wgrad_tc");
+  void (*kern)(const WgTcArgs) = opt_tc_uniform_issue() ? conv_wgrad_tc_kernel<true, false> : conv_wgrad_tc_kernel<false, false>;
+  if (accumulate) kern = conv_wgrad_tc_kernel<true, true>;
+  AVC_LAUNCH(kern, grid, 128, smem, (cudaStream_t)stream, a);
+  AVC_CHECK_LAUNCH(who);
+  if (accumulate) return AVC_OK;
   const int64_t n = (int64_t)d->K * (d->Cin / 4) * a.coutp;
   if (opt_wgrad_reduce_v2())
     AVC_LAUNCH(wgrad_tc_reduce_kernel<true>, (int)cdiv64(n, 32), dim3(32, 8), 0, (cudaStream_t)stream, scratch, d->dw, d->Cout, d->Cin, d->K, a.coutp, a.nslices);
   else
     AVC_LAUNCH(wgrad_tc_reduce_kernel<false>, (int)cdiv64(n, 32), dim3(32, 8), 0, (cudaStream_t)stream, scratch, d->dw, d->Cout, d->Cin, d->K, a.coutp, a.nslices);
   AVC_CHECK_LAUNCH("wgrad_tc_reduce");
+  return AVC_OK;
+}
+
+extern "C" int avc_conv_wgrad_tc(const avc_wgrad_desc* d, float* scratch, int* status, void* stream) {
+  return wgrad_tc_launch(d, scratch, status, stream, false, "avc_conv_wgrad_tc");
+}
+
+// ---- accumulate-in-place variant: every layer owns a zeroed [K][Cin/4][coutp][4] accumulation
+// buffer; avc_conv_wgrad_tc_acc adds into it (vector atomics), avc_wgrad_acc_flush folds every
+// layer's buffer into its nn.Conv1d gradient and zeroes it again -- ONE launch per backward pass.
+extern "C" int64_t avc_wgrad_acc_floats(int Cout, int Cin, int K) {
+  if (Cout <= 0 || Cin <= 0 || K <= 0 || Cin % 4 != 0) return -1;
+  return (int64_t)K * Cin * (cdiv(Cout, 128) * 128);
+}
+extern "C" int avc_conv_wgrad_tc_acc(const avc_wgrad_desc* d, float* acc, int* status, void* stream) {
+  return wgrad_tc_launch(d, acc, status, stream, true, "avc_conv_wgrad_tc_acc");
+}
+extern "C" int avc_wgrad_acc_flush(const avc_wgrad_acc_item* items_dev, int n_items, int64_t max_units, void* stream) {
+  AVC_REQUIRE(items_dev && n_items > 0 && max_units > 0, AVC_ERR_INVALID, "avc_wgrad_acc_flush: bad argument");
+  dim3 grid((unsigned)cdiv64(max_units, 256), (unsigned)n_items);
+  AVC_LAUNCH(wgrad_acc_flush_kernel, grid, 256, 0, (cudaStream_t)stream, items_dev);
+  AVC_CHECK_LAUNCH("wgrad_acc_flush");
   return AVC_OK;
 }

@@ -80,6 +80,11 @@ class Engine:
         # as one launch each (csrc/dense_fused.cu); off = one launch per nn.Linear
         self.fused_dense = os.environ.get("AVC_FUSED_DENSE", "1" if L.DEFAULT_FUSED_DENSE else "0") == "1"
         self._ptr_tables: Dict[tuple, tuple] = {}
+        # opt-in: conv weight gradients accumulate in place (vector atomics) and are folded into the
+        # nn.Conv1d gradients by ONE flush launch per backward pass; only on buffers registered with
+        # prepare_wgrad_acc (the trainer's persistent flat gradient)
+        self.wgrad_acc = os.environ.get("AVC_WGRAD_ACC", "1" if L.DEFAULT_WGRAD_ACC else "0") == "1"
+        self._wg_acc = None
         se, ce, de = config["SpeakerEncoder"], config["ContentEncoder"], config["Decoder"]
         for c in (se, ce):
             if c.get("act", "relu") != "relu" or c.get("dropout_rate", 0) != 0:
@@ -316,10 +321,57 @@ class Engine:
                        norm=norm, relu=relu, K=K, Cin=Cin, Cout=Cout, Tout=Tout, pl=pl, pr=pr)
         return out, rec
 
+    def prepare_wgrad_acc(self, P, G):
+        """Register the persistent gradient buffers G for in-place accumulation: one zeroed arena
+        with a [K][Cin/4][coutp][4] region per conv layer and the device item table of the flush
+        kernel.  Must run before a CUDA-graph capture (it copies the table to the device)."""
+        if not self.wgrad_acc or self.precision != "tf32":
+            self._wg_acc = None
+            return
+        names = [n for n in self.conv_names() if n + ".weight" in P and n + ".weight" in G]
+        key = tuple((G[n + ".weight"].data_ptr(), tuple(P[n + ".weight"].shape)) for n in names)
+        if self._wg_acc is not None and self._wg_acc["key"] == key:
+            return
+        offs, total, max_units, rows = {}, 0, 1, []
+        for n in names:
+            Cout, Cin, K = P[n + ".weight"].shape
+            nf = int(self.lib.avc_wgrad_acc_floats(Cout, Cin, K))
+            if nf <= 0 or Cout % 4 != 0:
+                continue
+            offs[n] = total
+            rows.append((n, total, Cout, Cin, K))
+            total += nf
+            max_units = max(max_units, nf // 4)
+        if not rows:
+            self._wg_acc = None
+            return
+        arena = self.zeros(total)
+        items = (L.WgradAccItem * len(rows))()
+        dw_ptr = {}
+        for it, (n, off, Cout, Cin, K) in zip(items, rows):
+            it.acc, it.dw = arena.data_ptr() + 4 * off, G[n + ".weight"].data_ptr()
+            it.Cout, it.Cin, it.K = Cout, Cin, K
+            dw_ptr[n] = it.dw
+        raw = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8).to(self.dev)
+        self._wg_acc = dict(key=key, arena=arena, offs=offs, dw_ptr=dw_ptr, items=raw, n=len(rows), max_units=max_units, dirty=False)
+
+    def flush_wgrad(self):
+        """Fold the accumulated conv weight gradients into the registered gradient buffers."""
+        acc = self._wg_acc
+        if acc is not None and acc["dirty"]:
+            self._ck(self.lib.avc_wgrad_acc_flush(acc["items"].data_ptr(), acc["n"], acc["max_units"], self.stream), "wgrad_acc_flush")
+            acc["dirty"] = False
+
     def wgrad(self, wd, name):
         """dW += conv weight gradient; tensor cores when the shape allows, FFMA otherwise."""
         if self.precision == "tf32":
             n = int(self.lib.avc_wgrad_tc_scratch_floats(C.byref(wd)))
+            acc = self._wg_acc
+            if n > 0 and acc is not None and acc["dw_ptr"].get(name) == wd.dw:
+                ptr = acc["arena"].data_ptr() + 4 * acc["offs"][name]
+                self._ck(self.lib.avc_conv_wgrad_tc_acc(C.byref(wd), ptr, self.tc_status.data_ptr(), self.stream), f"conv_wgrad_tc_acc[{name}]")
+                acc["dirty"] = True
+                return
             if n > 0:
                 scratch = self.empty(n)
                 self._ck(self.lib.avc_conv_wgrad_tc(C.byref(wd), scratch.data_ptr(), self.tc_status.data_ptr(), self.stream), f"conv_wgrad_tc[{name}]")

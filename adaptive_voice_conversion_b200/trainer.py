@@ -45,6 +45,7 @@ class FusedTrainer:
         self.launches_per_step = 0
         self.eng.pack_weights(self.P, need_dgrad=True)
         self.eng.prepare_tables(self.P, self.G)   # before any CUDA-graph capture
+        self.eng.prepare_wgrad_acc(self.P, self.G)
         self._lambda_kl = None
         opt.sync_hparams(lambda_rec=float(config["lambda"]["lambda_rec"]), lambda_kl=float(config["lambda"]["lambda_kl"]))
 
@@ -70,6 +71,7 @@ class FusedTrainer:
         dmu4, dls4 = eng.reparam_bwd(dz4, ls4, eps, dmu, dls)
         eng.content_bwd(P, G, ce, dmu4, dls4)
         eng.speaker_bwd(P, G, cs, demb)
+        eng.flush_wgrad()   # no-op unless weight gradients were accumulated in place (AVC_WGRAD_ACC=1)
         return mu, ls, emb, dec
 
     def _allreduce(self):
@@ -112,6 +114,7 @@ class FusedTrainer:
         (eager) steps first -- they DO update the parameters."""
         lam = self._lambda_kl if self._lambda_kl is not None else float(self.cfg["lambda"]["lambda_kl"])
         self.eng.prepare_tables(self.P, self.G)
+        self.eng.prepare_wgrad_acc(self.P, self.G)
         self._static = x_example.contiguous().clone()
         for _ in range(warmup):
             self.step(self._static, lam)

@@ -160,6 +160,20 @@ int avc_conv_wgrad(const avc_wgrad_desc* d, void* stream);
  * or -1 when the shape must use avc_conv_wgrad.  status as in avc_conv_block_tc. */
 int64_t avc_wgrad_tc_scratch_floats(const avc_wgrad_desc* d);
 int avc_conv_wgrad_tc(const avc_wgrad_desc* d, float* scratch, int* status, void* stream);
+/* Accumulate-in-place variant (opt-in, non-deterministic summation order): every conv layer owns a
+ * ZEROED buffer of avc_wgrad_acc_floats(Cout, Cin, K) floats; avc_conv_wgrad_tc_acc adds the
+ * layer's weight gradient into it with vector atomics (no scratch round trip, no per-layer
+ * reduction launch; d->dw is ignored) and avc_wgrad_acc_flush folds EVERY layer's buffer into its
+ * nn.Conv1d gradient (dw += ...) and zeroes it again, in one launch over a DEVICE item table;
+ * max_units = the largest avc_wgrad_acc_floats()/4 of the table. */
+typedef struct avc_wgrad_acc_item {
+  float* acc;
+  float* dw; /* [Cout][Cin][K] accumulated (+=) */
+  int32_t Cout, Cin, K, reserved;
+} avc_wgrad_acc_item;
+int64_t avc_wgrad_acc_floats(int Cout, int Cin, int K);
+int avc_conv_wgrad_tc_acc(const avc_wgrad_desc* d, float* acc, int* status, void* stream);
+int avc_wgrad_acc_flush(const avc_wgrad_acc_item* items_dev, int n_items, int64_t max_units, void* stream);
 
 /* Adjoint of the reflect padding + residual adjoint.  dxp is the zero-padded "full"
  * transposed conv output (length Tin + pad_left + pad_right) produced by
