@@ -23,6 +23,7 @@ run() {  # run <name> <timeout> <env...> -- <cmd...>
 run t2_W    120 $W $X -- $TESTS tests/test_gpu_wgrad_acc.py tests/test_gpu_tc_conv.py tests/test_gpu_model.py
 run b2_W     60 $W    -- $BENCH
 run b2_base  60       -- $BENCH
+run t2_props 120 $X   -- $TESTS tests/test_gpu_properties.py
 python - <<'PY'
 import json, glob, os
 for f in sorted(glob.glob("gpurun_out/b2_*.out")):
