@@ -106,18 +106,57 @@ class Solver(object):
         loss_rec, loss_kl, grad_norm = self.trainer.losses()
         return {"loss_rec": loss_rec, "loss_kl": loss_kl, "grad_norm": grad_norm}
 
+    # ---- input prefetch (opt-in, AVC_PREFETCH=1): the host-to-device copy of batch i+1 runs on a copy
+    # stream while step i computes; every step still copies its own batch and reads its own losses
+    def _prefetch(self, batch):
+        dev = local_device()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        with torch.cuda.stream(self._copy_stream):
+            x = batch.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        return x, ev
+
+    def run_steps(self, n_iterations, lambda_of=None, on_step=None):
+        """n optimizer steps on the training iterator; returns the last step's losses.
+        lambda_of(iteration) -> lambda_kl (default: the configured constant); on_step(iteration, meta,
+        lambda_kl) is called after every step."""
+        lam0 = self.config["lambda"]["lambda_kl"]
+        prefetch = os.environ.get("AVC_PREFETCH", "0") == "1"
+        nxt = self._prefetch(next(self.train_iter)) if prefetch else None
+        meta = None
+        for iteration in range(n_iterations):
+            lambda_kl = lam0 if lambda_of is None else lambda_of(iteration)
+            if prefetch:
+                x, ev = nxt
+                nxt = self._prefetch(next(self.train_iter))     # overlaps with this step
+                cur = torch.cuda.current_stream(x.device)
+                cur.wait_event(ev)
+                x.record_stream(cur)
+                self.trainer.step(x, lambda_kl)
+                loss_rec, loss_kl, grad_norm = self.trainer.losses()
+                meta = {"loss_rec": loss_rec, "loss_kl": loss_kl, "grad_norm": grad_norm}
+            else:
+                meta = self.ae_step(next(self.train_iter), lambda_kl)
+            if on_step is not None:
+                on_step(iteration, meta, lambda_kl)
+        return meta
+
     # ---- loop (solver.py:99-118)
     def train(self, n_iterations):
         lam = self.config["lambda"]["lambda_kl"]
         anneal = self.config["annealing_iters"]
-        for iteration in range(n_iterations):
-            lambda_kl = lam if iteration >= anneal else lam * (iteration + 1) / anneal
-            meta = self.ae_step(next(self.train_iter), lambda_kl)
-            if self.rank == 0:
-                if iteration % self.args.summary_steps == 0:
-                    self.logger.scalars_summary(f"{self.args.tag}/ae_train", meta, iteration)
-                print(f"AE:[{iteration + 1}/{n_iterations}], loss_rec={meta['loss_rec']:.2f}, "
-                      f"loss_kl={meta['loss_kl']:.2f}, lambda={lambda_kl:.1e}     ", end="\r")
-                if (iteration + 1) % self.args.save_steps == 0 or iteration + 1 == n_iterations:
-                    self.save_model(iteration=iteration)
-                    print()
+
+        def on_step(iteration, meta, lambda_kl):
+            if self.rank != 0:
+                return
+            if iteration % self.args.summary_steps == 0:
+                self.logger.scalars_summary(f"{self.args.tag}/ae_train", meta, iteration)
+            print(f"AE:[{iteration + 1}/{n_iterations}], loss_rec={meta['loss_rec']:.2f}, "
+                  f"loss_kl={meta['loss_kl']:.2f}, lambda={lambda_kl:.1e}     ", end="\r")
+            if (iteration + 1) % self.args.save_steps == 0 or iteration + 1 == n_iterations:
+                self.save_model(iteration=iteration)
+                print()
+
+        self.run_steps(n_iterations, lambda_of=lambda it: lam if it >= anneal else lam * (it + 1) / anneal, on_step=on_step)

@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--e2e-api", choices=["ae_step", "run_steps"], default="ae_step",
+                    help="public call timed by the e2e arm: Solver.ae_step per pinned host batch (default), or "
+                         "Solver.run_steps with the input prefetch on a copy stream (AVC_PREFETCH=1; opt-in until validated)")
     ap.add_argument("--workload", default="train", choices=["train", "inference"],
                     help="train: BASELINE config 3/4 (default, the headline metric); inference: config 5, 64 (src,tgt) pairs of 80x512")
     return ap.parse_args()
@@ -303,13 +306,20 @@ def run_b200(args):
         barrier()
         ms = e0.elapsed_time(e1)
         # ---- end-to-end arm through the public API, host batches
-        for i in range(2):
-            solver.ae_step(host_batches[i % len(host_batches)], 1.0)
+        if args.e2e_api == "run_steps":
+            os.environ["AVC_PREFETCH"] = "1"
+            solver.run_steps(2, lambda_of=lambda it: 1.0)
+        else:
+            for i in range(2):
+                solver.ae_step(host_batches[i % len(host_batches)], 1.0)
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
-        for i in range(K):
-            meta = solver.ae_step(host_batches[i % len(host_batches)], 1.0)
+        if args.e2e_api == "run_steps":
+            meta = solver.run_steps(K, lambda_of=lambda it: 1.0)
+        else:
+            for i in range(K):
+                meta = solver.ae_step(host_batches[i % len(host_batches)], 1.0)
         f1.record()
         barrier()
         ms_e2e = f0.elapsed_time(f1)
@@ -332,7 +342,8 @@ def run_b200(args):
                        "cuda_graph": not args.no_graph,
                        "l2": "per-step working set (~1.5 GB saved activations) >> 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": B * args.c_in * SEG_T * 4, "d2h_bytes_per_step": 16,
-                    "api": "Solver.ae_step(pinned host batch, lambda_kl) -> {'loss_rec','loss_kl','grad_norm'}"},
+                    "api": ("Solver.ae_step(pinned host batch, lambda_kl) -> {'loss_rec','loss_kl','grad_norm'}" if args.e2e_api == "ae_step" else
+                            "Solver.run_steps(K): pinned host batches, copy of batch i+1 overlaps step i, losses read every step")},
             "gpu_launches": int(launches_per_step) * K,
             "launches_per_step": int(launches_per_step),
             "clocks": clk.summary(),

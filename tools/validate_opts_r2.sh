@@ -24,6 +24,7 @@ run t2_W    120 $W $X -- $TESTS tests/test_gpu_wgrad_acc.py tests/test_gpu_tc_co
 run b2_W     60 $W    -- $BENCH
 run b2_base  60       -- $BENCH
 run t2_props 120 $X   -- $TESTS tests/test_gpu_properties.py
+run b2_prefetch 60    -- $BENCH --e2e-api run_steps
 python - <<'PY'
 import json, glob, os
 for f in sorted(glob.glob("gpurun_out/b2_*.out")):
