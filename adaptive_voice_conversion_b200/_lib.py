@@ -19,13 +19,16 @@ DEFAULT_FUSED_DENSE = True
 # engine.py: conv weight gradients accumulated in place with vector atomics + ONE flush launch per
 # backward pass (csrc/wgrad_tc.cu, ATOMIC); not yet run on a B200 -> opt in with AVC_WGRAD_ACC=1
 DEFAULT_WGRAD_ACC = False
+# engine.py: reflect-padding / residual adjoint inside the data-gradient conv's epilogue (AVC_F_FOLD, 37
+# avc_fold_add_fwd launches fewer per step); not yet run on a B200 -> opt in with AVC_FOLD_FUSED=1
+DEFAULT_FOLD_FUSED = False
 PDL = os.environ.get("AVC_PDL", "1" if DEFAULT_PDL else "0") == "1"
 LIB_PATH = os.environ.get("AVC_LIB", os.path.join(_PKG, "libavc_b200_pdl.so" if PDL else "libavc_b200.so"))
 
 PAD_REFLECT, PAD_ZERO = 0, 1
 RES_NONE, RES_SAME, RES_POOL, RES_UP = 0, 1, 2, 3
 PACK_FWD, PACK_DGRAD = 0, 1
-F_ROUND_OUT, F_IN_TF32 = 1, 2
+F_ROUND_OUT, F_IN_TF32, F_FOLD = 1, 2, 4
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
 
 _fp = C.c_void_p  # device pointers travel as integers

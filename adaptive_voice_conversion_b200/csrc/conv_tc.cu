@@ -87,7 +87,9 @@ __device__ __forceinline__ void issue_slab(uint32_t tb, uint32_t a_lo0, uint32_t
 
 // UI (uniform issue): warp index via lane-0 broadcast + election inside the MMA asm, see issue_slab.
 // UI = false is the round-1 issue loop (ELECT + VOTEU per MMA), kept selectable with AVC_TC_ISSUE=legacy.
-template <bool UI>
+// FOLD (AVC_F_FOLD, plain stride-1 data-gradient convs): the epilogue applies the adjoint of the forward
+// conv's reflect padding and of its residual branch itself (what avc_fold_add_fwd does in a second pass).
+template <bool UI, bool FOLD>
 __global__ void __launch_bounds__(512, 1) conv_block_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_full[TC_MAX_STAGES], bar_ready[TC_MAX_STAGES], bar_empty[TC_MAX_STAGES], bar_done;
@@ -313,6 +315,85 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc_kernel(const TcArgs a) {
         }
       }
       if (!active) continue;
+      if constexpr (FOLD) {
+        // D holds Tout = T + pl + pr columns of the zero-padded transposed conv (dxp); the input gradient
+        // is dx[t] = D[t+pl] + D[pl-t] (1 <= t <= pl) + D[2(T-1)-t+pl] (that column >= pl+T) + residual
+        // adjoint.  All mirrored columns belong to this thread's own TMEM lane.
+        const int fpl = (d.flags >> 8) & 0xff, fpr = (d.flags >> 16) & 0xff;
+        const int Tf = d.Tout - fpl - fpr;
+        const uint32_t col0 = lane_addr + (uint32_t)(g * a.npad);
+        float Le[4], Re[4];
+        {
+          float v0[16], v1[16], v2[16];
+          tc::tmem_ld16(col0, v0);
+          Le[0] = v0[0]; Le[1] = v0[1]; Le[2] = v0[2]; Le[3] = v0[3];
+          const int rc0 = ((fpl + Tf) >> 4) << 4, ro = fpl + Tf - rc0;   // chunk and offset of column pl+T
+          tc::tmem_ld16(col0 + (uint32_t)rc0, v1);
+          if (rc0 + 16 < a.npad) {
+            tc::tmem_ld16(col0 + (uint32_t)(rc0 + 16), v2);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v2[i] = 0.f;
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float r = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              r = (i == ro + e) ? v1[i] : r;
+              r = (i + 16 == ro + e) ? v2[i] : r;
+            }
+            Re[e] = e < fpr ? r : 0.f;
+          }
+        }
+        float* fobase = d.out + (size_t)b * d.out_bstride + ((size_t)cq * Tf) * 4;
+        const float* frb = d.res ? d.res + (size_t)b * d.res_bstride + ((size_t)cq * d.res_T) * 4 : nullptr;
+        const int ur = Tf - 2 + fpl;   // column that receives Re[0]; Re[e] goes to column ur - e
+        for (int c0 = cbeg; c0 < cend; c0 += 16) {
+          float v[16];
+          tc::tmem_ld16(col0 + (uint32_t)c0, v);
+          if (c0 == 0) {   // left halo: source column e -> target column 2*pl - e (2*pl <= 8 < 16)
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (e < fpl && i == 2 * fpl - e) v[i] += Le[e];
+          }
+          if (c0 + 16 > ur - 3 && c0 <= ur) {   // right halo
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (e < fpr && c0 + i == ur - e) v[i] += Re[e];
+          }
+#pragma unroll
+          for (int i4 = 0; i4 < 16; i4 += 4) {
+            float x0 = v[i4], x1 = v[i4 + 1], x2 = v[i4 + 2], x3 = v[i4 + 3];
+            quad_transpose(x0, x1, x2, x3, r4);
+            const int t = c0 + i4 + r4 - fpl;   // this lane now owns one time step of the quad's 4 channels
+            if (q_ok && t >= 0 && t < Tf) {
+              float4 o = make_float4(x0, x1, x2, x3);
+              if (frb) {   // adjoint of the forward residual branch (same cases as fold_add_kernel)
+                float4 r;
+                if (d.res_mode == AVC_RES_SAME) {
+                  r = ldg4(frb + (size_t)t * 4);
+                } else if (d.res_mode == AVC_RES_POOL) {
+                  r = ldg4(frb + (size_t)(t >> 1) * 4);
+                  const float wgt = ((Tf & 1) && t == Tf - 1) ? 1.f : 0.5f;
+                  r.x *= wgt; r.y *= wgt; r.z *= wgt; r.w *= wgt;
+                } else {
+                  r = ldg4(frb + (size_t)(2 * t) * 4);
+                  const float4 r2 = ldg4(frb + (size_t)(2 * t + 1) * 4);
+                  r.x += r2.x; r.y += r2.y; r.z += r2.z; r.w += r2.w;
+                }
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+              }
+              st4(fobase + (size_t)t * 4, o);
+            }
+          }
+        }
+        continue;
+      }
       float beta = 0.f, gamma = 1.f;
       if (d.cond && co_ok) {
         beta = __ldg(d.cond + (size_t)b * d.cond_bstride + cn);
@@ -526,6 +607,13 @@ extern "C" int avc_conv_block_tc(const avc_conv_desc* d, int* status, void* stre
   AVC_REQUIRE(d->out_tstride <= 1 || (!d->shuffle && !d->res && !d->mask && !d->norm), AVC_ERR_UNSUPPORTED,
               "avc_conv_block_tc: out_tstride only for plain (data-gradient) convs");
   AVC_REQUIRE(d->K >= 1 && d->K <= 8, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: K=%d not in 1..8", d->K);
+  if (d->flags & AVC_F_FOLD) {
+    const int fpl = (d->flags >> 8) & 0xff, fpr = (d->flags >> 16) & 0xff;
+    AVC_REQUIRE(d->stride == 1 && !d->norm && !d->relu && !d->shuffle && !d->cond && !d->mask && !d->save_c && !d->bias && d->out_tstride <= 1,
+                AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: AVC_F_FOLD is for plain stride-1 (data-gradient) convs");
+    AVC_REQUIRE(fpl <= 4 && fpr <= 4 && d->Tout - fpl - fpr >= 2 * fpl + 1 && d->Tout - fpl - fpr >= fpr + 2, AVC_ERR_UNSUPPORTED,
+                "avc_conv_block_tc: AVC_F_FOLD pads (%d,%d) do not fit %d columns", fpl, fpr, d->Tout);
+  }
   AVC_REQUIRE(d->Cin % TC_SLAB == 0, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: Cin %% 16 != 0");
   const int ncols_full = d->stride == 2 ? 2 * d->Tout - 1 : d->Tout;  // stride 2: full-resolution columns 0 .. 2(Tout-1)
   AVC_REQUIRE(ncols_full <= 256, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: more than 256 columns per sample");
@@ -560,8 +648,9 @@ extern "C" int avc_conv_block_tc(const avc_conv_desc* d, int* status, void* stre
   const int smem = a.nstage * (int)a.stage_bytes;
   static int attr_smem = 0;
   if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_block_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_block_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    cudaError_t e = cudaFuncSetAttribute(conv_block_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_block_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_block_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max);
     if (e != cudaSuccess) {
       set_error("avc_conv_block_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return AVC_ERR_CUDA;
@@ -569,8 +658,9 @@ extern "C" int avc_conv_block_tc(const avc_conv_desc* d, int* status, void* stre
     attr_smem = smem_max;
   }
   dim3 grid(cdiv(d->B, G), mtiles);
-  if (opt_tc_uniform_issue()) AVC_LAUNCH(conv_block_tc_kernel<true>, grid, 512, smem, (cudaStream_t)stream, a);
-  else AVC_LAUNCH(conv_block_tc_kernel<false>, grid, 512, smem, (cudaStream_t)stream, a);
+  void (*kern)(const TcArgs) = opt_tc_uniform_issue() ? conv_block_tc_kernel<true, false> : conv_block_tc_kernel<false, false>;
+  if (d->flags & AVC_F_FOLD) kern = conv_block_tc_kernel<true, true>;
+  AVC_LAUNCH(kern, grid, 512, smem, (cudaStream_t)stream, a);
   AVC_CHECK_LAUNCH("conv_block_tc");
   return AVC_OK;
 }

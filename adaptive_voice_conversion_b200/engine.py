@@ -76,15 +76,7 @@ class Engine:
             raise L.AvcError("AVC_PRECISION must be 'tf32' or 'fp32'")
         self.tc_status = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self._packed_key = None
-        # opt-in: the speaker dense stack as one kernel per direction and the 12 AdaIN affine layers
-        # as one launch each (csrc/dense_fused.cu); off = one launch per nn.Linear
-        self.fused_dense = os.environ.get("AVC_FUSED_DENSE", "1" if L.DEFAULT_FUSED_DENSE else "0") == "1"
-        self._ptr_tables: Dict[tuple, tuple] = {}
-        # opt-in: conv weight gradients accumulate in place (vector atomics) and are folded into the
-        # nn.Conv1d gradients by ONE flush launch per backward pass; only on buffers registered with
-        # prepare_wgrad_acc (the trainer's persistent flat gradient)
-        self.wgrad_acc = os.environ.get("AVC_WGRAD_ACC", "1" if L.DEFAULT_WGRAD_ACC else "0") == "1"
-        self._wg_acc = None
+        self._init_options()
         se, ce, de = config["SpeakerEncoder"], config["ContentEncoder"], config["Decoder"]
         for c in (se, ce):
             if c.get("act", "relu") != "relu" or c.get("dropout_rate", 0) != 0:
@@ -98,6 +90,21 @@ class Engine:
             for s in c["subsample"]:
                 if s not in (1, 2):
                     raise L.AvcError("subsample entries must be 1 or 2")
+
+    def _init_options(self):
+        """Path switches (environment defaults, see README): every one can also be set on the instance."""
+        # opt-in: the speaker dense stack as one kernel per direction and the 12 AdaIN affine layers
+        # as one launch each (csrc/dense_fused.cu); off = one launch per nn.Linear
+        self.fused_dense = os.environ.get("AVC_FUSED_DENSE", "1" if L.DEFAULT_FUSED_DENSE else "0") == "1"
+        self._ptr_tables: Dict[tuple, tuple] = {}
+        # opt-in: conv weight gradients accumulate in place (vector atomics) and are folded into the
+        # nn.Conv1d gradients by ONE flush launch per backward pass; only on buffers registered with
+        # prepare_wgrad_acc (the trainer's persistent flat gradient)
+        self.wgrad_acc = os.environ.get("AVC_WGRAD_ACC", "1" if L.DEFAULT_WGRAD_ACC else "0") == "1"
+        # opt-in: stride-1 data-gradient convs apply the reflect-padding / residual adjoint in their own
+        # epilogue (AVC_F_FOLD) instead of a separate avc_fold_add_fwd pass
+        self.fold_fused = os.environ.get("AVC_FOLD_FUSED", "1" if L.DEFAULT_FOLD_FUSED else "0") == "1"
+        self._wg_acc = None
 
     # ------------------------------------------------------------------ utilities
     @property
@@ -455,6 +462,16 @@ class Engine:
                 self._ck(self.lib.avc_conv_block_tc(C.byref(d), self.tc_status.data_ptr(), st), f"conv_dgrad_tc_s2[{name}]")
         elif (self.precision == "tf32" and stride == 1 and Cout % 16 == 0 and Lp <= 256 and "dgrad_tc" in self.packed[name]):
             d.w_tc = self.packed[name]["dgrad_tc"].data_ptr()
+            if self.fold_fused and not direct and xin.T >= 2 * rec["pl"] + 1 and xin.T >= rec["pr"] + 2:
+                # the data-gradient conv folds the reflect halo and the residual adjoint in its own epilogue
+                d.out, d.out_bstride, d.out_T = dx.ptr, dx.bstride, xin.T
+                d.flags = int(d.flags) | L.F_FOLD | (rec["pl"] << 8) | (rec["pr"] << 16)
+                if dres is not None:
+                    d.res, d.res_bstride, d.res_mode, d.res_T = dres.ptr, dres.bstride, dres_mode, dres.T
+                self._ck(self.lib.avc_conv_block_tc(C.byref(d), self.tc_status.data_ptr(), st), f"conv_dgrad_tc_fold[{name}]")
+                if self.debug:
+                    self.debug(name, "dx", dx)
+                return dx
             self._ck(self.lib.avc_conv_block_tc(C.byref(d), self.tc_status.data_ptr(), st), f"conv_dgrad_tc[{name}]")
         else:
             self._ensure_simt_pack(P, name, "dgrad")

@@ -49,6 +49,12 @@ extern "C" {
  * TF32 path rounds to nearest -- once, where an activation is produced. */
 #define AVC_F_ROUND_OUT 1 /* round out (conv block / norm_apply) or dc (norm_bwd) to TF32 */
 #define AVC_F_IN_TF32 2   /* `in` is already TF32-exact: avc_conv_block_tc skips its rounding pass */
+/* avc_conv_block_tc, plain stride-1 conv used as a data gradient: the epilogue also applies the
+ * adjoint of the forward conv's reflect padding (pl = (flags>>8)&255, pr = (flags>>16)&255) and of
+ * its residual branch (res / res_mode / res_T read as in avc_fold_desc): Tout = T+pl+pr columns are
+ * computed, `out` receives the T folded time steps (what avc_fold_add_fwd produces in a second pass). */
+#define AVC_F_FOLD 4
+#define AVC_FOLD_FLAGS(pl, pr) (AVC_F_FOLD | ((pl) << 8) | ((pr) << 16))
 
 #define AVC_PACK_FWD 0   /* P[ci][j][co]  = W[co][ci][j]                                   */
 #define AVC_PACK_DGRAD 1 /* P[co][j][ci]  = W[co][ci][K-1-j]  (transposed, tap-flipped)     */

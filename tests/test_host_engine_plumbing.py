@@ -32,7 +32,8 @@ def rig(monkeypatch):
     e = object.__new__(E.Engine)      # the real constructor insists on a CUDA device
     e.cfg, e.dev, e.lib, e.packed, e.debug = cfg, torch.device("cpu"), RecordingLib(), {}, None
     e.precision, e.tc_status, e._packed_key = "tf32", torch.zeros(1, dtype=torch.int32), None
-    e.fused_dense, e._ptr_tables, e.wgrad_acc, e._wg_acc = True, {}, False, None
+    e._init_options()
+    e.fused_dense, e.wgrad_acc, e.fold_fused = True, False, False
     monkeypatch.setattr(E.Engine, "stream", property(lambda self: 0))
     monkeypatch.setattr(E.Engine, "zeros", lambda self, *shape: torch.zeros(shape))
     P = orc.init_state(cfg, seed=0)
@@ -126,3 +127,17 @@ def test_runtime_options_roundtrip():
     assert L.get_option("no_such_option") == -1
     with pytest.raises(L.AvcError):
         L.set_option("no_such_option", True)
+
+
+def test_fused_fold_drops_the_fold_launches(rig):
+    e, P, G = rig
+    e.lib.calls.clear()
+    full_step(e, P, G)
+    n_fold, n_conv = e.lib.calls.count("avc_fold_add_fwd"), e.lib.calls.count("avc_conv_block_tc")
+    assert n_fold > 30
+    e.fold_fused = True
+    e.lib.calls.clear()
+    full_step(e, P, G)
+    # left: the 6 stride-2 data gradients (even/odd tap convs) and the one plain tensor add of content_bwd
+    assert e.lib.calls.count("avc_fold_add_fwd") == 7 and e.lib.calls.count("avc_conv_block_tc") == n_conv
+    assert n_fold - 7 == 30

@@ -2,11 +2,13 @@
 # Round-2 first GPU call: validate what was written without a GPU at the end of round 1
 # (gpurun --timeout 200 -- 'bash tools/validate_opts_r2.sh').  Same recipe as tools/validate_opts.sh.
 #   W = AVC_WGRAD_ACC=1   conv weight gradients accumulated in place (vector atomics) + one flush launch
+#   D = AVC_FOLD_FUSED=1  reflect-padding / residual adjoint inside the data-gradient conv epilogue
 set -u
 O=gpurun_out
 mkdir -p $O
 : > $O/val2_summary.txt
 W="AVC_WGRAD_ACC=1"
+D="AVC_FOLD_FUSED=1"
 X="AVC_TEST_EXPERIMENTAL=1"
 BENCH="python bench.py --steps 20 --warmup 5 --skip-cpu"
 TESTS="python -m pytest -q -m gpu -p no:cacheprovider"
@@ -23,6 +25,9 @@ run() {  # run <name> <timeout> <env...> -- <cmd...>
 run t2_W    120 $W $X -- $TESTS tests/test_gpu_wgrad_acc.py tests/test_gpu_tc_conv.py tests/test_gpu_model.py
 run b2_W     60 $W    -- $BENCH
 run b2_base  60       -- $BENCH
+run t2_D    120 $D $X -- $TESTS tests/test_gpu_fold_fused.py tests/test_gpu_model.py
+run b2_D     60 $D    -- $BENCH
+run b2_WD    60 $W $D -- $BENCH
 run t2_props 120 $X   -- $TESTS tests/test_gpu_properties.py
 run b2_prefetch 60    -- $BENCH --e2e-api run_steps
 python - <<'PY'
