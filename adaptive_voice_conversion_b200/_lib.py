@@ -9,21 +9,17 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-# AVC_PDL=1 selects the programmatic-dependent-launch build of the same sources
-# (libavc_b200_pdl.so, csrc/common.cuh).  Validated on the B200 (all parity tests green) but it
-# bought nothing inside the CUDA-graph step (42 068 vs 42 513 seg/s), so it stays opt-in.
-DEFAULT_PDL = False
 # engine.py: fused speaker dense stack / batched AdaIN affine layers (csrc/dense_fused.cu); ON since
 # the B200 validation run (42 513 -> 45 462 seg/s); AVC_FUSED_DENSE=0 = one launch per nn.Linear
 DEFAULT_FUSED_DENSE = True
 # engine.py: conv weight gradients accumulated in place with vector atomics + ONE flush launch per
-# backward pass (csrc/wgrad_tc.cu, ATOMIC); not yet run on a B200 -> opt in with AVC_WGRAD_ACC=1
-DEFAULT_WGRAD_ACC = False
-# engine.py: reflect-padding / residual adjoint inside the data-gradient conv's epilogue (AVC_F_FOLD, 37
-# avc_fold_add_fwd launches fewer per step); not yet run on a B200 -> opt in with AVC_FOLD_FUSED=1
-DEFAULT_FOLD_FUSED = False
-PDL = os.environ.get("AVC_PDL", "1" if DEFAULT_PDL else "0") == "1"
-LIB_PATH = os.environ.get("AVC_LIB", os.path.join(_PKG, "libavc_b200_pdl.so" if PDL else "libavc_b200.so"))
+# backward pass (csrc/wgrad_tc.cu, ATOMIC).  ON since the round-2 B200 validation (tests green, 45 649 ->
+# 49 658 seg/s); AVC_WGRAD_ACC=0 = per-slice partials + deterministic reduction
+DEFAULT_WGRAD_ACC = True
+# engine.py: reflect-padding / residual adjoint inside the data-gradient conv's epilogue (AVC_F_FOLD, 30
+# avc_fold_add_fwd launches fewer per step).  ON since the round-2 validation (tests green, +0.5 %)
+DEFAULT_FOLD_FUSED = True
+LIB_PATH = os.environ.get("AVC_LIB", os.path.join(_PKG, "libavc_b200.so"))
 
 PAD_REFLECT, PAD_ZERO = 0, 1
 RES_NONE, RES_SAME, RES_POOL, RES_UP = 0, 1, 2, 3

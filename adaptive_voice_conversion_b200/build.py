@@ -7,12 +7,15 @@ Every .cu under csrc/ is compiled to an object file (in parallel) with
 ``adaptive_voice_conversion_b200/libavc_b200.so``.  nvcc cross-compiles, so this works in
 the GPU-less authoring container; the .so travels to the GPU box with the tree.
 
-Two variants are built from the same sources: ``libavc_b200.so`` and ``libavc_b200_pdl.so``
-(``-DAVC_PDL=1``: programmatic dependent launch, see csrc/common.cuh); ``_lib.py`` picks one.
+Safe under ``torchrun``: the build takes an exclusive file lock (the other ranks wait, then find the
+stamp up to date) and every output is written to a temporary name and renamed into place, so no
+process can ever dlopen a half-written library.
 """
 from __future__ import annotations
 
 import argparse
+import contextlib
+import fcntl
 import hashlib
 import os
 import shutil
@@ -26,7 +29,6 @@ OBJ = os.path.join(PKG, "csrc", "_obj")
 LIB = os.path.join(PKG, "libavc_b200.so")
 VARIANTS = {  # name -> (library, object dir, extra nvcc flags)
     "default": (LIB, OBJ, []),
-    "pdl": (os.path.join(PKG, "libavc_b200_pdl.so"), os.path.join(PKG, "csrc", "_obj_pdl"), ["-DAVC_PDL=1"]),
 }
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
@@ -59,15 +61,47 @@ def headers():
     return hs
 
 
+@contextlib.contextmanager
+def _locked(path):
+    """Exclusive inter-process lock (all ranks of a torchrun launch share the tree)."""
+    with open(path, "a+") as f:
+        fcntl.flock(f, fcntl.LOCK_EX)
+        try:
+            yield
+        finally:
+            fcntl.flock(f, fcntl.LOCK_UN)
+
+
+def _write_atomic(path, text):
+    tmp = f"{path}.{os.getpid()}.tmp"
+    with open(tmp, "w") as f:
+        f.write(text)
+    os.replace(tmp, path)
+
+
+def _up_to_date(lib, stamp, dig):
+    try:
+        return os.path.exists(lib) and open(stamp).read() == dig
+    except OSError:
+        return False
+
+
 def build_variant(variant: str, force: bool = False, verbose: bool = False, allow_build: bool = True) -> str:
     lib, objdir, extra = VARIANTS[variant]
-    os.makedirs(objdir, exist_ok=True)
     stamp = os.path.join(objdir, "stamp.txt")
     dig = _digest(sources() + headers(), extra)
-    if not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read() == dig:
+    if not force and _up_to_date(lib, stamp, dig):
         return lib
     if not allow_build:
         raise RuntimeError(f"{lib} is missing or older than its sources and building was not allowed")
+    os.makedirs(objdir, exist_ok=True)
+    with _locked(os.path.join(objdir, "build.lock")):
+        if not force and _up_to_date(lib, stamp, dig):   # another rank built it while we waited
+            return lib
+        return _build_locked(lib, objdir, extra, stamp, dig, force, verbose)
+
+
+def _build_locked(lib, objdir, extra, stamp, dig, force, verbose):
     cc = nvcc()
     hdr_dig = _digest(headers(), extra)
 
@@ -77,7 +111,8 @@ def build_variant(variant: str, force: bool = False, verbose: bool = False, allo
         d = _digest([src], extra) + hdr_dig
         if not force and os.path.exists(obj) and os.path.exists(ostamp) and open(ostamp).read() == d:
             return obj
-        cmd = [cc, *ARCH, *FLAGS, *extra, "-c", src, "-o", obj]
+        tmp = f"{obj}.{os.getpid()}.tmp.o"
+        cmd = [cc, *ARCH, *FLAGS, *extra, "-c", src, "-o", tmp]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -85,23 +120,24 @@ def build_variant(variant: str, force: bool = False, verbose: bool = False, allo
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
         if verbose:
             sys.stderr.write(r.stderr)
-        with open(ostamp, "w") as f:
-            f.write(d)
+        os.replace(tmp, obj)
+        _write_atomic(ostamp, d)
         return obj
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, sources()))
-    cmd = [cc, *ARCH, "-shared", "-Xcompiler", "-fPIC", "-o", lib, *objs, "-lcudart"]
+    tmp_lib = f"{lib}.{os.getpid()}.tmp"
+    cmd = [cc, *ARCH, "-shared", "-Xcompiler", "-fPIC", "-o", tmp_lib, *objs, "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    with open(stamp, "w") as f:
-        f.write(dig)
+    os.replace(tmp_lib, lib)     # atomic: a concurrent dlopen sees the old or the new file, never a partial one
+    _write_atomic(stamp, dig)
     return lib
 
 
 def build(force: bool = False, verbose: bool = False, allow_build: bool = True) -> str:
-    """Build (or stamp-check) every variant; returns the default library's path."""
+    """Build (or stamp-check) the library; returns its path."""
     for v in VARIANTS:
         build_variant(v, force, verbose, allow_build)
     return LIB

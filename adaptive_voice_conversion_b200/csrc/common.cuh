@@ -10,46 +10,9 @@
 #error "libavc_b200 is written for sm_100a (B200) only"
 #endif
 
-// AVC_PDL=1 builds the programmatic-dependent-launch variant (libavc_b200_pdl.so): every kernel is
-// launched with cudaLaunchAttributeProgrammaticStreamSerialization and starts with pdl_sync(), so the
-// launch latency and prologue of kernel N+1 overlap the tail of kernel N (also as CUDA-graph edges).
-// AVC_PDL=0 compiles to exactly the plain <<<>>> launches and kernels of the default library.
-#ifndef AVC_PDL
-#define AVC_PDL 0
-#endif
-
 namespace avc {
 
-// Let the next kernel in the stream start launching, then wait until the previous one has completed
-// and flushed.  MUST precede the first global-memory access of a kernel; kernels that allocate
-// TMEM call it after the allocation (a dependent CTA parked in the wait must never hold TMEM
-// columns that a CTA of the still-running primary kernel is waiting to allocate).
-__device__ __forceinline__ void pdl_sync() {
-#if AVC_PDL
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-#endif
-}
-
-#if AVC_PDL
-template <typename... KArgs, typename... Args>
-inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface in AVC_CHECK_LAUNCH
-}
-#define AVC_LAUNCH(kern, grid, block, smem, st, ...) avc::launch_pdl(kern, grid, block, smem, st, __VA_ARGS__)
-#else
 #define AVC_LAUNCH(kern, grid, block, smem, st, ...) kern<<<grid, block, smem, st>>>(__VA_ARGS__)
-#endif
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);

@@ -183,7 +183,6 @@ __device__ __forceinline__ void conv_epilogue(float (&acc)[8][8], const ConvArgs
 
 template <int K, int S, int TCO, int TT>
 __global__ void __launch_bounds__(256, 2) conv_block_fwd_kernel(const ConvArgs a) {
-  pdl_sync();
   using C = ConvCfg<K, S, TCO, TT>;
   extern __shared__ __align__(16) float smem[];
   float* Xs = smem;                 // [CK][XROW] planar input rows (padding resolved)

@@ -117,7 +117,6 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc_kernel(const TcArgs a) {
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  pdl_sync();  // after the TMEM allocation, before the first global access (see common.cuh)
   const uint32_t tbase = tmem_slot;
   bool ok = true;
   long long tm0 = 0, tm1 = 0, tm2 = 0, dbg_acc0 = 0, dbg_acc1 = 0;
@@ -493,7 +492,6 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc_kernel(const TcArgs a) {
 // [tap][chunk 4][co 128][4 floats], TF32-rounded, zero padded: one contiguous bulk copy per stage.
 __global__ void pack_weight_tc_kernel(const float* __restrict__ w, float* __restrict__ p, int Cout, int Cin, int K, int mode,
                                       int co_total, int ci_total) {
-  pdl_sync();
   // mode FWD: conv(co', ci', j) = W[co'][ci'][j];  DGRAD: conv(co', ci', j) = W[ci'][co'][K-1-j]
   // co_total / ci_total: channel counts of the conv being packed (FWD: Cout/Cin, DGRAD: Cin/Cout)
   const int mt = (co_total + 127) / 128, nslab = (ci_total + TC_SLAB - 1) / TC_SLAB;
@@ -516,7 +514,6 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, float* __rest
 
 // All weight re-packs of a model in ONE launch: blockIdx.y walks a device-resident item table.
 __global__ void __launch_bounds__(256) pack_weights_batch_kernel(const avc_pack_item* __restrict__ items) {
-  pdl_sync();
   const avc_pack_item it = items[blockIdx.y];
   const int Cout = it.Cout, Cin = it.Cin, K = it.K;
   const int64_t nw = (int64_t)Cout * Cin * K;

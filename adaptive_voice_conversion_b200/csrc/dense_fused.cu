@@ -54,7 +54,6 @@ __device__ __forceinline__ void ds_dot_cols(const float (&w)[DS_C], const float 
 // save planes  [B][C]: 0..n: h_0..h_n (block inputs, h_n feeds the output layer) | n+1..2n: y_l =
 // relu(W1 h + b1) | 2n+1..3n: a_l = relu(W2 y + b2)
 __global__ void __launch_bounds__(DS_C) dense_stack_fwd_kernel(const avc_dense_stack_desc d) {
-  pdl_sync();
   __shared__ __align__(16) float h[DS_R][DS_C];
   __shared__ __align__(16) float y[DS_R][DS_C];
   const int n = threadIdx.x, r0 = blockIdx.x * DS_R;
@@ -116,7 +115,6 @@ __global__ void __launch_bounds__(DS_C) dense_stack_fwd_kernel(const avc_dense_s
 // gsave planes [B][C]: 0..n-1: g1_l (into W1_l) | n..2n-1: g2_l (into W2_l) | 2n: dout (into Wo);
 // each is the upstream gradient AFTER the layer's ReLU mask = the left operand of its weight gradient
 __global__ void __launch_bounds__(DS_C) dense_stack_bwd_kernel(const avc_dense_stack_desc d) {
-  pdl_sync();
   __shared__ __align__(16) float g[DS_R][DS_C];
   const int k = threadIdx.x, r0 = blockIdx.x * DS_R;
   const int nr = min(DS_R, d.B - r0), nb = d.n_blocks;
@@ -174,7 +172,6 @@ __global__ void __launch_bounds__(DS_C) dense_stack_bwd_kernel(const avc_dense_s
 // ------------------------------------------------------------------ L same-shape linears per launch
 // out_l[b][n] = W_l[n] . x_l[b] + bias_l[n];  block = 32 (n) x 8 (rows), grid.z = layer
 __global__ void __launch_bounds__(256) linear_batch_fwd_kernel(const avc_linear_batch_desc d) {
-  pdl_sync();
   __shared__ float xs[8][33];
   __shared__ float ws[32][33];
   const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
@@ -204,7 +201,6 @@ __global__ void __launch_bounds__(256) linear_batch_fwd_kernel(const avc_linear_
 
 // part[l][b][k] = sum_n g_l[b][n] W_l[n][k];  grid.z = layer
 __global__ void __launch_bounds__(256) linear_batch_dx_kernel(const avc_linear_batch_desc d) {
-  pdl_sync();
   __shared__ float gs[8][33];
   __shared__ float ws[32][33];
   const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
@@ -234,7 +230,6 @@ __global__ void __launch_bounds__(256) linear_batch_dx_kernel(const avc_linear_b
 // out[i] = sum_l part[l][i] (+ add[i])
 __global__ void __launch_bounds__(256) sum_slices_kernel(const float* __restrict__ part, int L, int64_t n, const float* __restrict__ add,
                                                          float* __restrict__ out) {
-  pdl_sync();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float s = add ? __ldg(add + i) : 0.f;
     for (int l = 0; l < L; ++l) s += __ldg(part + (int64_t)l * n + i);
@@ -244,7 +239,6 @@ __global__ void __launch_bounds__(256) sum_slices_kernel(const float* __restrict
 
 // dW_l[n][k] += sum_b g_l[b][n] x_l[b][k];  db_l[n] += sum_b g_l[b][n];  grid.z = layer
 __global__ void __launch_bounds__(256) linear_batch_dw_kernel(const avc_linear_batch_desc d) {
-  pdl_sync();
   __shared__ float gs[32][9];   // [b][n]
   __shared__ float xs[32][33];  // [b][k]
   const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;

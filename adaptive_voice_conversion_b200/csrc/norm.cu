@@ -44,7 +44,6 @@ __device__ __forceinline__ void load_rows(const float* cb /*sample base*/, int q
 
 template <bool SHUF>
 __global__ void __launch_bounds__(256) norm_apply_fwd_kernel(const avc_conv_desc d) {
-  pdl_sync();
   constexpr int NS = SHUF ? 2 : 1;
   const int Cn = SHUF ? d.Cout / 2 : d.Cout;
   const int Tn = SHUF ? d.Tout * 2 : d.Tout;
@@ -139,7 +138,6 @@ __global__ void __launch_bounds__(256) norm_apply_fwd_kernel(const avc_conv_desc
 
 template <bool SHUF>
 __global__ void __launch_bounds__(256) norm_bwd_kernel(const avc_conv_desc d) {
-  pdl_sync();
   constexpr int NS = SHUF ? 2 : 1;
   const int Cn = SHUF ? d.Cout / 2 : d.Cout;
   const int Tn = SHUF ? d.Tout * 2 : d.Tout;
@@ -250,7 +248,6 @@ __global__ void __launch_bounds__(256) norm_bwd_kernel(const avc_conv_desc d) {
 // norm_bwd for the common training shape (no pixel shuffle, Tout <= 128): the row of `c` and of
 // `dy` is read ONCE into registers (4 float4 each per lane) and reused by both passes.
 __global__ void __launch_bounds__(256) norm_bwd_cached_kernel(const avc_conv_desc d) {
-  pdl_sync();
   const int Cn = d.Cout, Tn = d.Tout, Cnq = Cn >> 2;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -334,7 +331,6 @@ __global__ void __launch_bounds__(256) norm_bwd_cached_kernel(const avc_conv_des
 }
 
 __global__ void __launch_bounds__(256) fold_add_kernel(const avc_fold_desc d) {
-  pdl_sync();
   const int Cq = d.C >> 2;
   const int64_t total = (int64_t)d.B * Cq * d.Tin;
   const int Lp = d.Tin + d.pad_left + d.pad_right;
@@ -378,7 +374,6 @@ __global__ void __launch_bounds__(256) fold_add_kernel(const avc_fold_desc d) {
 // grid (C/4 chunks, batch slices): block-reduce a slice of (b, t), one atomicAdd per channel
 __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ dc, int64_t bstride, float* __restrict__ dbias,
                                                         int B, int C, int T, int bps) {
-  pdl_sync();
   const int q = blockIdx.x;
   const int b0 = blockIdx.y * bps, b1 = min(B, b0 + bps);
   float4 s = zero4();

@@ -32,7 +32,6 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ------------------------------------------------------------------ weight packing
 __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ p, int Cout, int Cin, int K, int mode) {
-  pdl_sync();
   const int64_t n = (int64_t)Cout * Cin * K;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     // i indexes the PACKED tensor so that writes are coalesced
@@ -60,7 +59,6 @@ __device__ __forceinline__ float rna_tf32(float x) {
   return __uint_as_float(r);
 }
 __global__ void pack_a4_kernel(const float* __restrict__ pl, float* __restrict__ a4, int64_t bstride, int B, int C, int T, int rnd) {
-  pdl_sync();
   const int Cq = C >> 2;
   const int64_t n = (int64_t)B * Cq * T;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -74,7 +72,6 @@ __global__ void pack_a4_kernel(const float* __restrict__ pl, float* __restrict__
   }
 }
 __global__ void unpack_a4_kernel(const float* __restrict__ a4, int64_t bstride, float* __restrict__ pl, int B, int C, int T) {
-  pdl_sync();
   const int Cq = C >> 2;
   const int64_t n = (int64_t)B * Cq * T;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -89,7 +86,6 @@ __global__ void unpack_a4_kernel(const float* __restrict__ a4, int64_t bstride, 
 
 // ------------------------------------------------------------------ mean over time
 __global__ void time_mean_fwd_kernel(const float* __restrict__ a4, int64_t bstride, float* __restrict__ out, int B, int C, int T) {
-  pdl_sync();
   const int Cq = C >> 2;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= B * Cq) return;
@@ -106,7 +102,6 @@ __global__ void time_mean_fwd_kernel(const float* __restrict__ a4, int64_t bstri
   }
 }
 __global__ void time_mean_bwd_kernel(const float* __restrict__ dout, float* __restrict__ da4, int64_t bstride, int B, int C, int T) {
-  pdl_sync();
   const int Cq = C >> 2;
   const int64_t n = (int64_t)B * Cq * T;
   const float inv = 1.f / (float)T;
@@ -123,7 +118,6 @@ __global__ void time_mean_bwd_kernel(const float* __restrict__ dout, float* __re
 // ------------------------------------------------------------------ small linear layers
 // block = 32 (n or k) x 8 (rows); tiles of 32 along the reduction dim staged in smem.
 __global__ void __launch_bounds__(256) linear_fwd_kernel(const avc_linear_desc d) {
-  pdl_sync();
   __shared__ float xs[8][33];
   __shared__ float ws[32][33];
   const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
@@ -162,7 +156,6 @@ __device__ __forceinline__ float masked_dy(const avc_linear_desc& d, int b, int 
 
 // dx[b][k] = sum_n g[b][n] W[n][k] (+ dx_add)
 __global__ void __launch_bounds__(256) linear_bwd_dx_kernel(const avc_linear_desc d) {
-  pdl_sync();
   __shared__ float gs[8][33];
   __shared__ float ws[32][33];
   const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
@@ -192,7 +185,6 @@ __global__ void __launch_bounds__(256) linear_bwd_dx_kernel(const avc_linear_des
 
 // dW[n][k] += sum_b g[b][n] x[b][k];  db[n] += sum_b g[b][n]
 __global__ void __launch_bounds__(256) linear_bwd_dw_kernel(const avc_linear_desc d) {
-  pdl_sync();
   __shared__ float gs[32][9];   // [b][n]
   __shared__ float xs[32][33];  // [b][k]
   const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
@@ -224,7 +216,6 @@ __global__ void __launch_bounds__(256) linear_bwd_dw_kernel(const avc_linear_des
 // ------------------------------------------------------------------ reparameterisation
 __global__ void reparam_fwd_kernel(const float* __restrict__ mu4, const float* __restrict__ ls4, const float* __restrict__ eps,
                                    float* __restrict__ mu, float* __restrict__ ls, float* __restrict__ z4, int B, int C, int T) {
-  pdl_sync();
   const int Cq = C >> 2;
   const int64_t n = (int64_t)B * Cq * T;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -249,7 +240,6 @@ __global__ void reparam_fwd_kernel(const float* __restrict__ mu4, const float* _
 __global__ void reparam_bwd_kernel(const float* __restrict__ dz4, const float* __restrict__ ls4, const float* __restrict__ eps,
                                    const float* __restrict__ dmu_ext, const float* __restrict__ dls_ext,
                                    float* __restrict__ dmu4, float* __restrict__ dls4, int B, int C, int T) {
-  pdl_sync();
   const int Cq = C >> 2;
   const int64_t n = (int64_t)B * Cq * T;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -292,7 +282,6 @@ __global__ void __launch_bounds__(256) vae_loss_kernel(const float* __restrict__
                                                        const float* __restrict__ mu, const float* __restrict__ ls, int64_t n_lat,
                                                        const float* __restrict__ hp, float* __restrict__ sums,
                                                        float* __restrict__ ddec, float* __restrict__ dmu, float* __restrict__ dls) {
-  pdl_sync();
   __shared__ float sh[8];
   const float lrec = hp[0], lkl = hp[1];
   const float grec = lrec / (float)n_rec, gkl = lkl / (float)n_lat;
@@ -320,7 +309,6 @@ __global__ void __launch_bounds__(256) vae_loss_kernel(const float* __restrict__
 
 // ------------------------------------------------------------------ grad norm + Adam
 __global__ void __launch_bounds__(256) sqnorm_stage1(const float* __restrict__ g, int64_t n, float* __restrict__ scratch) {
-  pdl_sync();
   __shared__ float sh[8];
   float s = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -331,7 +319,6 @@ __global__ void __launch_bounds__(256) sqnorm_stage1(const float* __restrict__ g
   if (threadIdx.x == 0) scratch[blockIdx.x] = r;
 }
 __global__ void __launch_bounds__(256) sqnorm_stage2(const float* __restrict__ scratch, int nb, float* __restrict__ out) {
-  pdl_sync();
   __shared__ float sh[8];
   float s = 0.f;
   for (int i = threadIdx.x; i < nb; i += blockDim.x) s += scratch[i];
@@ -340,7 +327,6 @@ __global__ void __launch_bounds__(256) sqnorm_stage2(const float* __restrict__ s
 }
 
 __global__ void step_inc_kernel(float* step) {
-  pdl_sync();
   step[0] += 1.f;
 }
 
@@ -348,7 +334,6 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
                                                    float* __restrict__ v, float* __restrict__ vmax, int64_t n,
                                                    const float* __restrict__ hp, const float* __restrict__ sqnorm,
                                                    const float* __restrict__ step) {
-  pdl_sync();
   const float gscale = hp[2], lr = hp[3], b1 = hp[4], b2 = hp[5], eps = hp[6], wd = hp[7], max_norm = hp[8];
   const bool amsgrad = hp[9] != 0.f;
   const float gnorm = gscale * sqrtf(sqnorm[0]);
@@ -430,11 +415,7 @@ using namespace avc;
 
 extern "C" const char* avc_last_error(void) { return g_err; }
 extern "C" const char* avc_build_info(void) {
-#if AVC_PDL
-  return "libavc_b200 sm_100a (compute_100a) fp32-ffma + tcgen05 paths, pdl (programmatic dependent launch)";
-#else
   return "libavc_b200 sm_100a (compute_100a) fp32-ffma + tcgen05 paths";
-#endif
 }
 extern "C" int64_t avc_launch_count(void) { return (int64_t)g_launches.load(); }
 

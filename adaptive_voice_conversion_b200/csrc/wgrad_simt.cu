@@ -16,7 +16,6 @@ struct WgradArgs {
 };
 
 __global__ void __launch_bounds__(256, 2) conv_wgrad_kernel(const WgradArgs a) {
-  pdl_sync();
   __shared__ __align__(16) float As[WG_TK * WG_LD];  // dc  [t][co]
   __shared__ __align__(16) float Bs[WG_TK * WG_LD];  // x   [t][ci] (tap-shifted, reflect-padded)
   const avc_wgrad_desc& d = a.d;

@@ -76,7 +76,6 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  pdl_sync();  // after the TMEM allocation, before the first global access (see common.cuh)
   const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_slot, 0);
   const uint32_t atomA = (uint32_t)a.RA * 128u, atomX = (uint32_t)a.RX * 128u;
   const uint32_t idesc = tc::make_idesc_tf32(128, a.ntpad, 1, 1);
@@ -241,7 +240,6 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
 template <bool V2>
 __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __restrict__ scratch, float* __restrict__ dw, int Cout, int Cin,
                                                               int K, int coutp, int nslices) {
-  pdl_sync();
   __shared__ float4 part[8][32];
   const int64_t n = (int64_t)K * (Cin >> 2) * coutp;
   const int64_t slice_stride = n * 4;
@@ -283,7 +281,6 @@ __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __res
 // dW[co][ci][j] += acc[j][ci/4][co][ci%4]; acc = 0.   grid.y = layer (device item table), grid.x
 // covers the largest layer (smaller layers exit early)
 __global__ void __launch_bounds__(256) wgrad_acc_flush_kernel(const avc_wgrad_acc_item* __restrict__ items) {
-  pdl_sync();
   const avc_wgrad_acc_item it = items[blockIdx.y];
   const int coutp = cdiv(it.Cout, 128) * 128;
   const int64_t n = (int64_t)it.K * (it.Cin >> 2) * coutp;

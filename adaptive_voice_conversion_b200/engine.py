@@ -276,7 +276,11 @@ class Engine:
 
     # ------------------------------------------------------------------ one conv block
     def conv(self, P, name, xin: A4, *, stride=1, shuffle=False, norm=False, cond=None, relu=False,
-             res: Optional[A4] = None, res_mode=L.RES_NONE, out: Optional[A4] = None, train=False):
+             res: Optional[A4] = None, res_mode=L.RES_NONE, out: Optional[A4] = None, train=False, round_out=False):
+        """One fused conv block.  round_out (tf32 mode only): round the block output to TF32 -- set ONLY when
+        every consumer of `out` is a tensor-core conv operand (the first conv of a block, the bank convs), so
+        that the consumer can skip its rounding pass.  The residual stream, the mean/std heads and out_conv
+        stay full fp32 like the reference's activations (cuDNN-TF32 rounds matmul inputs only)."""
         w = P[name + ".weight"]
         Cout, Cin, K = w.shape
         assert Cin == xin.C, (name, Cin, xin.C)
@@ -303,8 +307,8 @@ class Engine:
         d.bias = P[name + ".bias"].data_ptr()
         d.eps = IN_EPS
         if self.precision == "tf32":
-            d.flags = L.F_ROUND_OUT | (L.F_IN_TF32 if xin.tf32 else 0)
-            if out.bstride == out.C * out.T:
+            d.flags = (L.F_ROUND_OUT if round_out else 0) | (L.F_IN_TF32 if xin.tf32 else 0)
+            if round_out and out.bstride == out.C * out.T:
                 out.tf32 = True
         if fused:
             self._fill_epilogue(d, out, shuffle, norm, relu, cond, res, res_mode, stats)
@@ -538,7 +542,8 @@ class Engine:
         self.pack_a4(x_planar, x4)
         recs = []
         for i, _k in enumerate(ks):
-            _, r = self.conv(P, f"{enc}.conv_bank.{i}", x4, relu=True, out=cat.channels(i * c_bank, (i + 1) * c_bank), train=False)
+            _, r = self.conv(P, f"{enc}.conv_bank.{i}", x4, relu=True, out=cat.channels(i * c_bank, (i + 1) * c_bank), train=False,
+                             round_out=True)   # the concat is read by in_conv (and its weight gradient) only
             recs.append(r)
         # every writer of `cat` (pack_a4 and the bank convs' epilogues) rounds to TF32 in tf32 mode
         cat.tf32 = self.precision == "tf32"
@@ -551,7 +556,7 @@ class Engine:
     def _enc_blocks(self, P, enc, c, out: A4, norm: bool, train: bool, ctx: dict):
         blocks = []
         for l, s in enumerate(c["subsample"][: c["n_conv_blocks"]]):
-            y, r1 = self.conv(P, f"{enc}.first_conv_layers.{l}", out, norm=norm, relu=True, train=train)
+            y, r1 = self.conv(P, f"{enc}.first_conv_layers.{l}", out, norm=norm, relu=True, train=train, round_out=True)
             new, r2 = self.conv(P, f"{enc}.second_conv_layers.{l}", y, stride=s, norm=norm, relu=True, res=out,
                                 res_mode=L.RES_POOL if s > 1 else L.RES_SAME, train=train)
             blocks.append((r1, r2, s, out))
@@ -728,7 +733,8 @@ class Engine:
                 aff.append(r)
         blocks = []
         for l, up in enumerate(c["upsample"][:nblk]):
-            y, r1 = self.conv(P, f"{dn}.first_conv_layers.{l}", out, norm=True, cond=conds[:, 2 * l], relu=True, train=train)
+            y, r1 = self.conv(P, f"{dn}.first_conv_layers.{l}", out, norm=True, cond=conds[:, 2 * l], relu=True, train=train,
+                              round_out=True)
             new, r2 = self.conv(P, f"{dn}.second_conv_layers.{l}", y, shuffle=(up > 1), norm=True, cond=conds[:, 2 * l + 1],
                                 relu=True, res=out, res_mode=L.RES_UP if up > 1 else L.RES_SAME, train=train)
             blocks.append((r1, r2, up))

@@ -40,7 +40,7 @@ class FusedAdam(torch.optim.Adam):
         self.scratch = torch.zeros(1024, dtype=torch.float32, device=dev)
         self.max_norm = float(max_norm)
         self.world_size = int(world_size)
-        self.hp_host = torch.zeros(HP_SIZE, dtype=torch.float32).pin_memory() if torch.cuda.is_available() else torch.zeros(HP_SIZE)
+        self.hp_host = torch.zeros(HP_SIZE, dtype=torch.float32)   # pageable on purpose, see sync_hparams
         self.hp = torch.zeros(HP_SIZE, dtype=torch.float32, device=dev)
         self._views()
         self.sync_hparams()
@@ -75,7 +75,10 @@ class FusedAdam(torch.optim.Adam):
         h[HP_LR], h[HP_B1], h[HP_B2] = g["lr"], g["betas"][0], g["betas"][1]
         h[HP_EPS], h[HP_WD], h[HP_MAXNORM] = g["eps"], g["weight_decay"], self.max_norm
         h[HP_AMSGRAD] = 1.0 if g["amsgrad"] else 0.0
-        self.hp.copy_(h, non_blocking=True)
+        # 64 bytes from PAGEABLE memory: the driver stages the bytes before the call returns, so the host
+        # vector may be rewritten for the next step (per-iteration KL annealing) while this copy is still
+        # queued behind the previous step -- a pinned source with non_blocking=True would race
+        self.hp.copy_(h)
 
     def zero_grad(self, set_to_none: bool = True):
         st = torch.cuda.current_stream(self.flat_g.device).cuda_stream

@@ -10,6 +10,7 @@ written by rank 0 only.  ``args.data_dir == 'synthetic'`` trains on N(0,1) segme
 """
 from __future__ import annotations
 
+import json
 import os
 
 import torch
@@ -37,6 +38,7 @@ class Solver(object):
             print(config)
             print(args)
         self.logger = Logger(getattr(args, "logdir", "log/")) if self.rank == 0 else None
+        self.iteration = 0   # optimizer steps done so far (checkpointed: the KL-annealing position survives a resume)
         self.get_data_loaders()
         self.build_model()
         if self.rank == 0 and getattr(args, "store_model_path", None):
@@ -46,10 +48,15 @@ class Solver(object):
 
     # ---- checkpoints (solver.py:39-55)
     def save_model(self, iteration):
+        """<path>.ckpt / <path>.opt exactly as the reference writes them (solver.py:39-43) plus <path>.iter:
+        the number of steps done.  The reference drops `iteration`, so a resumed run restarts its KL
+        annealing from zero (solver.py:100-104); here load_model restores it."""
         if self.rank != 0:
             return
         torch.save(self.model.state_dict(), f"{self.args.store_model_path}.ckpt")
         torch.save(self.opt.state_dict(), f"{self.args.store_model_path}.opt")
+        with open(f"{self.args.store_model_path}.iter", "w") as f:
+            json.dump({"iteration": int(iteration) + 1}, f)
 
     def save_config(self):
         with open(f"{self.args.store_model_path}.config.yaml", "w") as f:
@@ -65,6 +72,10 @@ class Solver(object):
         opt_path = f"{self.args.load_model_path}.opt"
         if os.path.exists(opt_path):
             self.opt.load_state_dict(torch.load(opt_path, map_location=dev))
+        it_path = f"{self.args.load_model_path}.iter"
+        if os.path.exists(it_path):    # absent for checkpoints written by the reference: start at 0 like it does
+            with open(it_path) as f:
+                self.iteration = int(json.load(f)["iteration"])
         self.trainer.eng.pack_weights(self.trainer.P, need_dgrad=True)
 
     # ---- data (solver.py:57-68)
@@ -106,8 +117,11 @@ class Solver(object):
         loss_rec, loss_kl, grad_norm = self.trainer.losses()
         return {"loss_rec": loss_rec, "loss_kl": loss_kl, "grad_norm": grad_norm}
 
-    # ---- input prefetch (opt-in, AVC_PREFETCH=1): the host-to-device copy of batch i+1 runs on a copy
-    # stream while step i computes; every step still copies its own batch and reads its own losses
+    # ---- the training loop's data path (replaces the reference's per-step `.to(device)` + `.item()` stalls,
+    # solver.py:82-97): the host-to-device copy of batch i+1 runs on a copy stream while step i computes, and
+    # step i's losses are read (16 bytes, pinned) only after step i+1 has been enqueued, so the GPU never waits
+    # for the host.  Every step still copies its own batch and reports its own losses.  AVC_PIPELINE=0 selects
+    # the plain loop (ae_step per batch).
     def _prefetch(self, batch):
         dev = local_device()
         if getattr(self, "_copy_stream", None) is None:
@@ -121,41 +135,63 @@ class Solver(object):
     def run_steps(self, n_iterations, lambda_of=None, on_step=None):
         """n optimizer steps on the training iterator; returns the last step's losses.
         lambda_of(iteration) -> lambda_kl (default: the configured constant); on_step(iteration, meta,
-        lambda_kl) is called after every step."""
+        lambda_kl) is called for every step (one step late when pipelined).  `iteration` counts from
+        self.iteration (0, or the checkpointed position after load_model)."""
         lam0 = self.config["lambda"]["lambda_kl"]
-        prefetch = os.environ.get("AVC_PREFETCH", "0") == "1"
-        nxt = self._prefetch(next(self.train_iter)) if prefetch else None
+        pipelined = os.environ.get("AVC_PIPELINE", "1") == "1"
         meta = None
-        for iteration in range(n_iterations):
-            lambda_kl = lam0 if lambda_of is None else lambda_of(iteration)
-            if prefetch:
-                x, ev = nxt
-                nxt = self._prefetch(next(self.train_iter))     # overlaps with this step
-                cur = torch.cuda.current_stream(x.device)
-                cur.wait_event(ev)
-                x.record_stream(cur)
-                self.trainer.step(x, lambda_kl)
-                loss_rec, loss_kl, grad_norm = self.trainer.losses()
-                meta = {"loss_rec": loss_rec, "loss_kl": loss_kl, "grad_norm": grad_norm}
-            else:
+        if not pipelined:
+            for iteration in range(self.iteration, self.iteration + n_iterations):
+                lambda_kl = lam0 if lambda_of is None else lambda_of(iteration)
                 meta = self.ae_step(next(self.train_iter), lambda_kl)
+                self.iteration = iteration + 1
+                if on_step is not None:
+                    on_step(iteration, meta, lambda_kl)
+            return meta
+
+        def finish(p):
+            it_, lam_, get = p
+            loss_rec, loss_kl, grad_norm = get()
+            m = {"loss_rec": loss_rec, "loss_kl": loss_kl, "grad_norm": grad_norm}
+            self.iteration = it_ + 1
             if on_step is not None:
-                on_step(iteration, meta, lambda_kl)
+                on_step(it_, m, lam_)
+            return m
+
+        start, end = self.iteration, self.iteration + n_iterations
+        nxt = self._prefetch(next(self.train_iter)) if n_iterations > 0 else None
+        pending = None
+        for iteration in range(start, end):
+            lambda_kl = lam0 if lambda_of is None else lambda_of(iteration)
+            x, ev = nxt
+            cur = torch.cuda.current_stream(x.device)
+            cur.wait_event(ev)
+            x.record_stream(cur)
+            self.trainer.step(x, lambda_kl)
+            get = self.trainer.losses_async()
+            if iteration + 1 < end:
+                nxt = self._prefetch(next(self.train_iter))     # overlaps with this step
+            if pending is not None:
+                meta = finish(pending)                          # step i-1's losses, read while step i runs
+            pending = (iteration, lambda_kl, get)
+        if pending is not None:
+            meta = finish(pending)
         return meta
 
     # ---- loop (solver.py:99-118)
     def train(self, n_iterations):
         lam = self.config["lambda"]["lambda_kl"]
         anneal = self.config["annealing_iters"]
+        last = self.iteration + n_iterations
 
         def on_step(iteration, meta, lambda_kl):
             if self.rank != 0:
                 return
             if iteration % self.args.summary_steps == 0:
                 self.logger.scalars_summary(f"{self.args.tag}/ae_train", meta, iteration)
-            print(f"AE:[{iteration + 1}/{n_iterations}], loss_rec={meta['loss_rec']:.2f}, "
+            print(f"AE:[{iteration + 1}/{last}], loss_rec={meta['loss_rec']:.2f}, "
                   f"loss_kl={meta['loss_kl']:.2f}, lambda={lambda_kl:.1e}     ", end="\r")
-            if (iteration + 1) % self.args.save_steps == 0 or iteration + 1 == n_iterations:
+            if (iteration + 1) % self.args.save_steps == 0 or iteration + 1 == last:
                 self.save_model(iteration=iteration)
                 print()
 

@@ -47,6 +47,9 @@ class FusedTrainer:
         self.eng.prepare_tables(self.P, self.G)   # before any CUDA-graph capture
         self.eng.prepare_wgrad_acc(self.P, self.G)
         self._lambda_kl = None
+        self._hp_key = None
+        self._static_eps = None
+        self._host_ring = None
         opt.sync_hparams(lambda_rec=float(config["lambda"]["lambda_rec"]), lambda_kl=float(config["lambda"]["lambda_kl"]))
 
     # ------------------------------------------------------------------ pieces
@@ -83,7 +86,12 @@ class FusedTrainer:
         self.eng.pack_weights(self.P, need_dgrad=True)
 
     def set_lambda_kl(self, lambda_kl: float):
-        if lambda_kl != self._lambda_kl:
+        """Push lambda_kl and the optimizer's param_group hyper-parameters (an lr scheduler may have changed
+        them) to the device vector the kernels read -- only when something changed."""
+        g = self.opt.param_groups[0]
+        key = (float(lambda_kl), g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"], bool(g["amsgrad"]))
+        if key != self._hp_key:
+            self._hp_key = key
             self._lambda_kl = lambda_kl
             self.opt.sync_hparams(lambda_kl=float(lambda_kl))
 
@@ -95,9 +103,12 @@ class FusedTrainer:
             raise L.AvcError("FusedTrainer.step: x must be a float32 CUDA tensor")
         x = x.contiguous()
         self.set_lambda_kl(lambda_kl)
-        if self._graphs is not None and eps is None and tuple(x.shape) == tuple(self._static.shape):
+        replay = self._graphs is not None and tuple(x.shape) == tuple(self._static.shape) and not return_outputs
+        if replay and (eps is None) == (self._static_eps is None):
             if x.data_ptr() != self._static.data_ptr():
                 self._static.copy_(x, non_blocking=True)
+            if eps is not None and eps.data_ptr() != self._static_eps.data_ptr():
+                self._static_eps.copy_(eps, non_blocking=True)
             self._graphs[0].replay()
             self._allreduce()
             self._graphs[1].replay()
@@ -109,30 +120,54 @@ class FusedTrainer:
         self.launches_per_step = L.launch_count() - n0
         return outs if return_outputs else None
 
-    def capture(self, x_example: torch.Tensor, warmup: int = 2):
+    def capture(self, x_example: torch.Tensor, warmup: int = 2, eps_example: Optional[torch.Tensor] = None):
         """Capture the step for x_example's shape into CUDA graphs.  Runs `warmup` real
-        (eager) steps first -- they DO update the parameters."""
+        (eager) steps first -- they DO update the parameters.  With eps_example the graph reads the
+        reparameterisation noise from a static buffer that step(x, lambda_kl, eps=...) refills (parity
+        tests inject eps); without it eps is drawn inside the graph from torch's device generator."""
         lam = self._lambda_kl if self._lambda_kl is not None else float(self.cfg["lambda"]["lambda_kl"])
         self.eng.prepare_tables(self.P, self.G)
         self.eng.prepare_wgrad_acc(self.P, self.G)
+        self._graphs = None
         self._static = x_example.contiguous().clone()
+        self._static_eps = None if eps_example is None else eps_example.contiguous().clone()
         for _ in range(warmup):
-            self.step(self._static, lam)
+            self.step(self._static, lam, eps=self._static_eps)
         torch.cuda.synchronize(self.dev)
         ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         pool = torch.cuda.graph_pool_handle()
         with torch.cuda.graph(ga, pool=pool):
-            self._fwd_bwd(self._static, None)
+            self._fwd_bwd(self._static, self._static_eps)
         with torch.cuda.graph(gb, pool=pool):
             self._update()
         self._graphs = (ga, gb)
         return self._static
 
-    def losses(self):
-        """(loss_rec, loss_kl, grad_norm) as Python floats -- synchronises."""
+    def _decode_report(self, r):
         import struct
-        r = self.report.tolist()     # the only synchronisation of a step
         status = struct.unpack("<i", struct.pack("<f", r[3]))[0]
         if status != 0:              # a tcgen05 pipeline barrier time-out must not go unnoticed
             raise L.AvcError(f"tcgen05 conv pipeline barrier timed out (code {status})")
         return r[0] / self.n_rec, 0.5 * r[1] / self.n_lat, (r[2] ** 0.5) / self.world
+
+    def losses(self):
+        """(loss_rec, loss_kl, grad_norm) as Python floats -- synchronises."""
+        return self._decode_report(self.report.tolist())     # the only synchronisation of a step
+
+    def losses_async(self):
+        """Enqueue the 16-byte device->host read of this step's report block behind the step and return a
+        handle; ``handle()`` waits for THAT copy only (not for work enqueued later) and returns
+        (loss_rec, loss_kl, grad_norm).  Lets a training loop enqueue step i+1 before it reads step i."""
+        if self._host_ring is None:
+            self._host_ring = [torch.zeros(4, dtype=torch.float32).pin_memory() for _ in range(4)]
+            self._ring_i = 0
+        slot = self._host_ring[self._ring_i % len(self._host_ring)]
+        self._ring_i += 1
+        slot.copy_(self.report, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+
+        def get():
+            ev.synchronize()
+            return self._decode_report(slot.tolist())
+        return get

@@ -54,9 +54,12 @@ def parse():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--e2e-api", choices=["ae_step", "run_steps"], default="ae_step",
-                    help="public call timed by the e2e arm: Solver.ae_step per pinned host batch (default), or "
-                         "Solver.run_steps with the input prefetch on a copy stream (AVC_PREFETCH=1; opt-in until validated)")
+    ap.add_argument("--skip-extras", action="store_true", help="skip the extra configurations (fp32 path, c_in=512, inference) of the N=1 line")
+    ap.add_argument("--windows", type=int, default=3, help="timed windows of --steps steps each; the median window is reported")
+    ap.add_argument("--e2e-api", choices=["ae_step", "run_steps"], default="run_steps",
+                    help="public call timed by the e2e arm: Solver.run_steps (the loop body of Solver.train: pinned host batch "
+                         "copied per step, losses read per step, copy/read pipelined one step deep; default), or Solver.ae_step "
+                         "per pinned host batch (the reference's blocking call)")
     ap.add_argument("--workload", default="train", choices=["train", "inference"],
                     help="train: BASELINE config 3/4 (default, the headline metric); inference: config 5, 64 (src,tgt) pairs of 80x512")
     return ap.parse_args()
@@ -67,6 +70,13 @@ def config_for(c_in, batch):
     cfg = default_config(c_in)
     cfg["data_loader"]["batch_size"] = batch
     return cfg
+
+
+def workload_config(args, world):
+    """`config` of the JSON line -- the same dict on the product arm and on the reference arm."""
+    B = args.batch
+    return {"workload": f"Solver.ae_step fwd+bwd+clip+Adam(amsgrad), batch {B}/GPU of {args.c_in}-mel x 128-frame segments (BASELINE config 3/4)",
+            "global_batch": B * world, "per_gpu_batch": B, "c_in": args.c_in, "parallelism": f"dp{world}"}
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -176,17 +186,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_b = 64
+    sample_b = args.batch          # the product arm's per-GPU batch: same config on both arms
     steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 2))
     rate, spt, cores = cpu_reference_rate(args.c_in, sample_b, steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": spt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic N(0,1) segments, random-init weights (seed 0)",
-        "config": {"workload": f"Solver.ae_step fwd+bwd+clip+Adam(amsgrad), {args.c_in}-mel x 128-frame segments", "global_batch": sample_b,
-                   "c_in": args.c_in, "parallelism": "cpu"},
+        "config": dict(workload_config(args, max(1, args.gpus)), executed_on="host CPU (reference arm)"),
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{steps} steps of batch {sample_b} (oracle port of the reference, torch CPU fp32, best of a thread sweep: {cores} of {os.cpu_count()} threads)"},
+                         "sample": f"{steps} steps of one GPU's batch ({sample_b} segments) after {warmup} warm-up (oracle port of the reference Solver.ae_step, torch CPU fp32, best of a thread sweep: {cores} of {os.cpu_count()} threads)"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -238,23 +247,34 @@ def dominant_kernel_roofline(dev, batch):
     except Exception:
         pass
     peak_tf = float(peaks.get("bf16_tflops", 1590.0))
-    src = "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if peaks else "fallback 1.59 PFLOP/s (B200_PROFILING.md)"
-    ach = flops / (avg_ms * 1e-3) / 1e12
-    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
-    try:
-        m = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_full_conv_block_tc.json")))
-        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        traffic = sum(float(m[k][0]) * scale[m[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum")) if eng.precision == "tf32" else None
-    except Exception:
-        pass
-    return {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": traffic,
+    peak_hbm = float(peaks.get("hbm_gbs", 6650.0))
+    src = ("measured (MEASURED_PEAKS.json: hbm_gbs copy bandwidth; bf16_tflops burst for the tensor keys)" if peaks
+           else "fallback 6.65 TB/s / 1.59 PFLOP/s (B200_PROFILING.md)")
+    tf = flops / (avg_ms * 1e-3) / 1e12
+    gbs = alg_bytes / (avg_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
+    if eng.precision == "tf32":
+        for name in ("r2_ncu_full_conv_block_tc.json", "r1_ncu_full_conv_block_tc.json"):
+            try:
+                m = json.load(open(os.path.join(ROOT, "profiles", name)))
+                scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                traffic = sum(float(m[k][0]) * scale[m[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                traffic_src = "profiles/" + name
+                break
+            except Exception:
+                continue
+    # Governing roofline: at the TF32 tensor rate (half the bf16 rate) this block needs ~4.7 us of tensor time
+    # but ~7.7 us of HBM time for its algorithmic bytes (x in once, c and y out once, weights) -> HBM-bound.
+    return {"bound": "hbm", "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm, "traffic": traffic,
+            "traffic_source": traffic_src,
             "kernel": ("conv_block_tc_kernel (tcgen05 TF32: fused reflect-pad conv k5 128->128 + InstanceNorm + ReLU, saves c)" if eng.precision == "tf32"
                        else "conv_block_fwd_kernel<5,1,128,128> (same block, fp32 FFMA path)"),
-            "avg_launch_ms": avg_ms, "alg_flops_per_launch": flops, "alg_bytes_per_launch": alg_bytes,
-            "hbm_gbs_at_alg_bytes": alg_bytes / (avg_ms * 1e-3) / 1e9, "peak_source": src,
-            "precision": eng.precision,
-            "hbm_frac_at_alg_bytes": alg_bytes / (avg_ms * 1e-3) / 1e9 / float(peaks.get("hbm_gbs", 6650.0)),
-            "note": "peak = measured dense bf16 tensor throughput; the kernel runs kind::tf32 (hardware rate = half of bf16, so frac <= 0.5 by construction). At TF32 rate the block needs 4.7 us of tensor time and 7.7 us of HBM time for its 50.7 MB of algorithmic bytes, so HBM is the governing roofline: hbm_frac_at_alg_bytes. traffic (ncu) is below the algorithmic bytes because the 33.6 MB of outputs stay in the 126 MB L2 during the capture"}
+            "shape": f"B={batch}, 128->128, k=5, T={T}",
+            "avg_launch_ms": avg_ms, "alg_bytes_per_launch": alg_bytes, "alg_flops_per_launch": flops,
+            "alg_bytes_note": "read x 16.8 MB + write c (saved for backward) 16.8 MB + write y 16.8 MB + weights 0.33 MB",
+            "tensor_tflops": tf, "tensor_frac_of_bf16_peak": tf / peak_tf, "tensor_frac_of_tf32_rate": tf / (0.5 * peak_tf),
+            "peak_source": src, "precision": eng.precision,
+            "timing": "CUDA graph of 20 back-to-back launches on rotating >L2 inputs (10 x 16.8 MB), CUDA events on the launching stream"}
 
 
 # ----------------------------------------------------------------------------- main arm
@@ -290,44 +310,53 @@ def run_b200(args):
             torch.distributed.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- device-resident arm
+    # ---- device-resident arm: NWIN windows of exactly K steps, each bracketed by barrier + synchronize; the
+    # reported window is the MEDIAN one (a single 0.1 s window is at the mercy of one straggler rank)
     if not args.no_graph:
         tr.capture(x_dev, warmup=2)
     for _ in range(W):
         tr.step(x_dev, 1.0)
     launches_per_step = tr.launches_per_step
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        e0.record()
+    NWIN = max(1, args.windows)
+
+    def timed_windows(run_k):
+        out = []
+        for _ in range(NWIN):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            meta_ = run_k()
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)   # max over ranks, per window
+            out.append(float(t[0]))
+        return out, meta_
+
+    def run_resident():
         for _ in range(K):
             tr.step(x_dev, 1.0)
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
+
+    def run_e2e():
+        if args.e2e_api == "run_steps":
+            return solver.run_steps(K, lambda_of=lambda it: 1.0)
+        for i in range(K):
+            m = solver.ae_step(host_batches[i % len(host_batches)], 1.0)
+        return m
+
+    with ClockSampler(local) as clk:
+        win, _ = timed_windows(run_resident)
         # ---- end-to-end arm through the public API, host batches
         if args.e2e_api == "run_steps":
-            os.environ["AVC_PREFETCH"] = "1"
             solver.run_steps(2, lambda_of=lambda it: 1.0)
         else:
             for i in range(2):
                 solver.ae_step(host_batches[i % len(host_batches)], 1.0)
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        if args.e2e_api == "run_steps":
-            meta = solver.run_steps(K, lambda_of=lambda it: 1.0)
-        else:
-            for i in range(K):
-                meta = solver.ae_step(host_batches[i % len(host_batches)], 1.0)
-        f1.record()
-        barrier()
-        ms_e2e = f0.elapsed_time(f1)
-    t = torch.tensor([ms, ms_e2e], device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+        win_e2e, meta = timed_windows(run_e2e)
+    ms, ms_e2e = sorted(win)[len(win) // 2], sorted(win_e2e)[len(win_e2e) // 2]
     finite = all(map(lambda v: v == v and abs(v) != float("inf"), meta.values()))
+    precision = tr.eng.precision
 
     if rank == 0:
         value = B * world * K / (ms * 1e-3)
@@ -335,15 +364,17 @@ def run_b200(args):
         roof = dominant_kernel_roofline(dev, B)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            # arithmetic type of the conv path: tcgen05 kind::tf32 (TF32 operands, fp32 accumulate) or exact fp32 FFMA
+            "dtype": "tf32" if precision == "tf32" else "f32",
             "data": "synthetic N(0,1) segments, random-init weights",
-            "config": {"workload": f"Solver.ae_step fwd+bwd+clip+Adam(amsgrad), batch {B}/GPU of {args.c_in}-mel x 128-frame segments (BASELINE config 3/4)",
-                       "global_batch": B * world, "per_gpu_batch": B, "c_in": args.c_in, "parallelism": f"dp{world}",
-                       "cuda_graph": not args.no_graph,
-                       "l2": "per-step working set (~1.5 GB saved activations) >> 126 MB L2; no explicit flush"},
+            "config": dict(workload_config(args, world), cuda_graph=not args.no_graph,
+                           l2="per-step working set (~1.5 GB saved activations) >> 126 MB L2; no explicit flush"),
+            "timing": {"windows": NWIN, "steps_per_window": K, "reported": "median window",
+                       "window_ms": win, "e2e_window_ms": win_e2e},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": B * args.c_in * SEG_T * 4, "d2h_bytes_per_step": 16,
                     "api": ("Solver.ae_step(pinned host batch, lambda_kl) -> {'loss_rec','loss_kl','grad_norm'}" if args.e2e_api == "ae_step" else
-                            "Solver.run_steps(K): pinned host batches, copy of batch i+1 overlaps step i, losses read every step")},
+                            "Solver.run_steps(K) (= the loop of Solver.train): every step copies its own pinned host batch to the device and reads its own 16-byte loss report; the copy of batch i+1 and the read of step i-1 overlap step i")},
             "gpu_launches": int(launches_per_step) * K,
             "launches_per_step": int(launches_per_step),
             "clocks": clk.summary(),
@@ -351,30 +382,86 @@ def run_b200(args):
             "last_losses": meta, "losses_finite": finite,
             "build": L.load().avc_build_info().decode(),
         }
-        if not args.skip_cpu:
-            rate, spt, cores = cpu_reference_rate(args.c_in, B, 3, 1)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"3 steps of batch {B} after 1 warm-up (oracle port of the reference Solver.ae_step, torch CPU fp32, best of a thread sweep: {cores} of {os.cpu_count()} threads), {spt:.2f} s/step"}
-        print(json.dumps(line), flush=True)
+    del solver, tr
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
+    if rank != 0:
+        return
+    if world == 1 and not args.skip_extras:
+        line["extras"] = extra_lines(args, dev)
+    if world == 1 and not args.skip_cpu:   # cpu_baseline: rank 0 at N=1 only (no rank spins on a barrier meanwhile)
+        rate, spt, cores = cpu_reference_rate(args.c_in, B, 3, 1)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"3 steps of batch {B} after 1 warm-up (oracle port of the reference Solver.ae_step, torch CPU fp32, best of a thread sweep: {cores} of {os.cpu_count()} threads), {spt:.2f} s/step"}
+    print(json.dumps(line), flush=True)
 
 
-def run_inference(args):
+def _quick_train_rate(c_in, batch, dev, steps, precision=None):
+    """seg/s of the graph-replayed step for one more configuration (device-resident, CUDA events)."""
+    import types, contextlib, io
+    from adaptive_voice_conversion_b200.solver import Solver
+    old = os.environ.get("AVC_PRECISION")
+    if precision:
+        os.environ["AVC_PRECISION"] = precision
+    try:
+        sargs = types.SimpleNamespace(data_dir="synthetic", train_set="", train_index_file="", logdir="/tmp/avc_log", load_model=False,
+                                      load_opt=False, store_model_path=None, load_model_path=None, summary_steps=10 ** 9,
+                                      save_steps=10 ** 9, tag="bench", iters=0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            solver = Solver(config_for(c_in, batch), sargs)
+        tr = solver.trainer
+        x = solver.train_loader.batches[0].to(dev)
+        tr.capture(x, warmup=2)
+        for _ in range(3):
+            tr.step(x, 1.0)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            tr.step(x, 1.0)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        tr.losses()
+        ms = e0.elapsed_time(e1) / steps
+        return {"value": batch / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "precision": tr.eng.precision,
+                "launches_per_step": int(tr.launches_per_step)}
+    finally:
+        if precision:
+            if old is None:
+                os.environ.pop("AVC_PRECISION", None)
+            else:
+                os.environ["AVC_PRECISION"] = old
+
+
+def extra_lines(args, dev):
+    """Other configurations, measured in the same run (N=1): the exact-fp32 path, the shipped config.yaml
+    (c_in=512) and BASELINE config 5 (inference).  Each is a short device-resident measurement."""
+    out = {}
+    legs = (("train_fp32_path", lambda: _quick_train_rate(args.c_in, args.batch, dev, 5, "fp32")),
+            ("train_c_in_512", lambda: _quick_train_rate(512, args.batch, dev, 10)),
+            ("inference_config5", lambda: inference_rates(args.c_in, 10, 3, skip_cpu=True)))
+    for name, fn in legs:
+        try:
+            out[name] = fn()
+        except Exception as e:   # an extra must never take the headline line down
+            out[name] = {"error": repr(e)[:200]}
+        torch.cuda.empty_cache()
+    return out
+
+
+def inference_rates(c_in, K, W, skip_cpu=False):
     """BASELINE config 5: one-shot VC on 64 synthetic (src, tgt) 80-mel utterance pairs of 512
     frames through Inferencer.inference_batch; utterances/s, device-resident and e2e (host pairs)."""
     import types
-    import oracle.ae_oracle as orc
     from adaptive_voice_conversion_b200.inference import Inferencer
     dev = torch.device("cuda", 0)
-    cfg = config_for(args.c_in, 64)
+    cfg = config_for(c_in, 64)
     inf = Inferencer(cfg, types.SimpleNamespace(attr=None, model=None, source=None, target=None, output=None, sample_rate=24000))
     g = torch.Generator().manual_seed(3)
-    xs = torch.randn((64, args.c_in, 512), generator=g).pin_memory()
-    xc = torch.randn((64, args.c_in, 512), generator=g).pin_memory()
+    xs = torch.randn((64, c_in, 512), generator=g).pin_memory()
+    xc = torch.randn((64, c_in, 512), generator=g).pin_memory()
     xd, cd = xs.to(dev), xc.to(dev)
-    K, W = args.steps, max(args.warmup, 3)
     for _ in range(W):
         out = inf.inference_batch(xd, cd)
     torch.cuda.synchronize()
@@ -392,13 +479,16 @@ def run_inference(args):
     f1.record()
     torch.cuda.synchronize()
     ms2 = f0.elapsed_time(f1)
+    inf.model.engine(dev).check_tc_status()
+    precision = inf.model.engine(dev).precision
     line = {"metric": "inference utts/sec (one-shot VC, 80-mel x 512-frame pairs)", "value": 64 * K / (ms * 1e-3), "unit": "utterances/s",
             "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic N(0,1) mels, random-init weights",
+            "dtype": "tf32" if precision == "tf32" else "f32", "data": "synthetic N(0,1) mels, random-init weights",
             "config": {"workload": "AE.inference, 64 (src,tgt) pairs of 80x512 (BASELINE config 5)", "global_batch": 64},
             "e2e": {"value": 64 * K / (ms2 * 1e-3), "unit": "utterances/s", "h2d_bytes_per_step": 2 * xs.numel() * 4, "d2h_bytes_per_step": host.numel() * 4},
-            "precision": inf.model.engine(dev).precision}
-    if not args.skip_cpu:
+            "precision": precision}
+    if not skip_cpu:
+        import oracle.ae_oracle as orc
         torch.set_num_threads(min(16, os.cpu_count() or 1))
         sd = orc.init_state(cfg, seed=0)
         with torch.no_grad():
@@ -408,7 +498,11 @@ def run_inference(args):
             dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": 64 / dt, "unit": "utterances/s", "cores": min(16, os.cpu_count() or 1), "kind": "port",
                                 "sample": "one batched pass over the 64 pairs (oracle port, torch CPU fp32)"}
-    print(json.dumps(line), flush=True)
+    return line
+
+
+def run_inference(args):
+    print(json.dumps(inference_rates(args.c_in, args.steps, max(args.warmup, 3), args.skip_cpu)), flush=True)
 
 
 def main():

@@ -46,22 +46,3 @@ def test_sass_is_sm100a():
     from adaptive_voice_conversion_b200 import _lib as L
     out = subprocess.run(["cuobjdump", "-lelf", L.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out, out
-
-
-def test_pdl_variant_exports_the_same_abi():
-    """libavc_b200_pdl.so (-DAVC_PDL=1, programmatic dependent launch) is built from the same
-    sources: same symbols, and only it carries the griddepcontrol instructions."""
-    import ctypes, subprocess
-    from adaptive_voice_conversion_b200 import build as B
-    B.build()
-    pdl = ctypes.CDLL(B.VARIANTS["pdl"][0])
-    for name in header_functions():
-        assert getattr(pdl, name) is not None
-    pdl.avc_build_info.restype = ctypes.c_char_p
-    assert b"pdl" in pdl.avc_build_info()
-    def count(lib):
-        sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN3avc22norm_bwd_cached_kernelE13avc_conv_desc", lib],
-                              capture_output=True, text=True).stdout
-        assert "EXIT" in sass, "kernel not found in " + lib
-        return sass.count("ACQBULK")
-    assert count(B.VARIANTS["pdl"][0]) >= 1 and count(B.VARIANTS["default"][0]) == 0

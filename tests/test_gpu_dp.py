@@ -1,0 +1,96 @@
+"""GPU: BASELINE config 4 semantics on the REAL trainer (trainer.FusedTrainer._allreduce, the 1/world scale folded
+into clip + Adam, graph A / all-reduce / graph B ordering): a world_size-2 step on two half batches equals the
+single-process step on the concatenated batch (solver.py:90-93 order), eps injected.
+
+Two ranks as subprocesses: nccl with one GPU per rank when the box has >= 2 GPUs, otherwise both ranks on
+cuda:0 with gloo all-reducing the CUDA gradient buffer (the code under test is the same)."""
+import os
+import socket
+import subprocess
+import sys
+import types
+
+import pytest
+import torch
+
+import oracle.ae_oracle as orc
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+PER_RANK = 8
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def rel_l2(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _single_process_reference(tmp_path):
+    from adaptive_voice_conversion_b200.solver import Solver
+    cfg = orc.default_config(80)
+    n = 2 * PER_RANK
+    cfg["data_loader"]["batch_size"] = n
+    args = types.SimpleNamespace(data_dir="synthetic", train_set="train", train_index_file="", logdir=str(tmp_path / "log"),
+                                 load_model=False, load_opt=False, store_model_path=str(tmp_path / "m1"),
+                                 load_model_path=str(tmp_path / "m1"), summary_steps=1, save_steps=10 ** 9, tag="t", iters=0)
+    solver = Solver(cfg, args)
+    solver.model.load_state_dict(orc.init_state(cfg, seed=0), strict=True)
+    solver.trainer.eng.pack_weights(solver.trainer.P, need_dgrad=True)
+    x = torch.randn((n, 80, 128), generator=torch.Generator().manual_seed(1)).cuda()
+    recs = []
+    for it in range(2):
+        eps = torch.randn((n, 128, 16), generator=torch.Generator().manual_seed(50 + it)).cuda()
+        solver.trainer.step(x, 0.37, eps=eps)
+        lr_, lk_, gn_ = solver.trainer.losses()
+        recs.append(dict(loss_rec=lr_, loss_kl=lk_, grad_norm=gn_, flat_g=solver.opt.flat_g.detach().cpu().clone(),
+                         flat_p=solver.opt.flat_p.detach().cpu().clone()))
+    return recs
+
+
+@pytest.mark.parametrize("mode", ["eager", "graph"])
+def test_two_rank_step_equals_single_process_step(tmp_path, mode):
+    ref = _single_process_reference(tmp_path)
+    ngpu = torch.cuda.device_count()
+    backend = "nccl" if ngpu >= 2 else "gloo"
+    port = _free_port()
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank if ngpu >= 2 else 0),
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "_dp_worker.py"), str(tmp_path), backend, str(PER_RANK), mode],
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    for p in procs:
+        try:
+            outs.append(p.communicate(timeout=600)[0])
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o[-3000:]
+    r0 = torch.load(str(tmp_path / "rank0.pt"))
+    r1 = torch.load(str(tmp_path / "rank1.pt"))
+    for it in range(2):
+        a, b, s = r0[it], r1[it], ref[it]
+        # replicas stay bit-identical: same all-reduced gradient, same update
+        assert torch.equal(a["flat_g"], b["flat_g"]) and torch.equal(a["flat_p"], b["flat_p"])
+        # the flat gradient buffer holds the SUM over ranks of per-rank means; 1/world lives in the clip/Adam kernel
+        assert rel_l2(0.5 * a["flat_g"], s["flat_g"]) < 2e-4, (it, rel_l2(0.5 * a["flat_g"], s["flat_g"]))
+        assert abs(a["grad_norm"] - s["grad_norm"]) / s["grad_norm"] < 2e-4
+        # losses are per-rank (each rank reports its own shard, like the reference under DDP): their mean is the global loss
+        for k in ("loss_rec", "loss_kl"):
+            assert abs(0.5 * (a[k] + b[k]) - s[k]) / s[k] < 1e-5, (it, k)
+        # post-step weights: Adam moves every element by ~lr * sign(g) on the first steps, so gradient noise at the
+        # 1e-4 level flips a few near-zero elements by 2*lr; compare against the size of one update
+        dp = float((a["flat_p"] - s["flat_p"]).abs().max())
+        assert dp <= 2.1 * 5e-4 * (it + 1), (it, dp)
+        assert rel_l2(a["flat_p"], s["flat_p"]) < 1e-4

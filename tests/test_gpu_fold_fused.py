@@ -1,6 +1,6 @@
 """GPU: the data-gradient conv with the reflect-padding / residual adjoint folded into its epilogue
 (AVC_F_FOLD, csrc/conv_tc.cu) against the two-pass path (conv + avc_fold_add_fwd) and autograd.
-Opt-in path, not yet run on a B200: AVC_TEST_EXPERIMENTAL=1 enables the file."""
+Default path since the round-2 B200 validation."""
 import math
 import os
 
@@ -11,8 +11,7 @@ import torch.nn.functional as F
 import oracle.ae_oracle as orc
 from test_gpu_kernels import relerr, rnd, to_a4, from_a4
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("AVC_TEST_EXPERIMENTAL") != "1", reason="experimental path: set AVC_TEST_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")

@@ -175,8 +175,48 @@ def test_solver_step_vs_oracle(tmp_path, precision):
     assert float(ref_opt.state_dict()["state"][0]["step"]) == 2.0
 
 
+def test_solver_step_b256_vs_oracle(tmp_path):
+    """BASELINE config 3 at FULL size: one Solver.ae_step on batch=256 (the fused step, default precision) vs the
+    oracle's train step on the same x / eps: losses within the 1e-3 contract, gradient norm, gradient (relative
+    L2) and post-step weights."""
+    from adaptive_voice_conversion_b200.solver import Solver
+    B = 256
+    cfg = orc.default_config(80)
+    cfg["data_loader"]["batch_size"] = B
+    solver = Solver(cfg, _solver_args(tmp_path))
+    sd = orc.init_state(cfg, seed=0)
+    solver.model.load_state_dict(sd, strict=True)
+    solver.trainer.eng.pack_weights(solver.trainer.P, need_dgrad=True)
+    st = orc.AdamState(sd)
+    x = torch.randn((B, 80, 128), generator=torch.Generator().manual_seed(1))
+    eps = torch.randn((B, 128, 16), generator=torch.Generator().manual_seed(2))
+    before = {k: v.detach().cpu().clone() for k, v in solver.model.state_dict().items()}
+    res = orc.ae_train_step(sd, st, cfg, x, eps, 1.0)          # sd is updated in place
+    meta = solver.ae_step(x, 1.0, eps=eps.cuda())
+    prec = solver.trainer.eng.precision
+    assert abs(meta["loss_rec"] - res["loss_rec"]) / res["loss_rec"] < REL
+    assert abs(meta["loss_kl"] - res["loss_kl"]) / res["loss_kl"] < REL
+    assert abs(meta["grad_norm"] - res["grad_norm"]) / res["grad_norm"] < tol(prec, 1e-2, 3e-2)
+    G = {k: v.detach().cpu().clone() for k, v in solver.trainer.G.items()}
+    assert_grads_close(G, res["grads"], list(sd), per_tensor=tol(prec, 5e-2, 3e-1), overall=tol(prec, 1e-2, 1e-1))
+    # the optimizer applied to OUR gradients lands on OUR weights (clip coefficient, bias correction, amsgrad, wd)
+    st2 = orc.AdamState(before)
+    gn = orc.clip_and_adam(before, G, st2, cfg["optimizer"])
+    assert abs(gn - meta["grad_norm"]) / gn < 1e-4
+    after = solver.model.state_dict()
+    for k in before:
+        assert float((after[k].cpu() - before[k]).abs().max()) < 2e-6, k
+    # and the reference's post-step weights: one Adam step moves every element by <= lr, so two correct
+    # implementations differ by at most 2*lr where the gradient sign is noise
+    lr = cfg["optimizer"]["lr"]
+    for k in sd:
+        assert float((after[k].cpu() - sd[k]).abs().max()) <= 2.05 * lr, k
+    solver.trainer.eng.check_tc_status()
+
+
 def test_graph_step_matches_eager(tmp_path):
-    """CUDA-graph replay of the fused step == eager step (same eps via reseeding)."""
+    """CUDA-graph replay of the fused step == the eager step, step by step, on injected eps (the graph reads
+    x and eps from static buffers refilled by step())."""
     from adaptive_voice_conversion_b200.solver import Solver
     outs = []
     for use_graph in (False, True):
@@ -185,17 +225,47 @@ def test_graph_step_matches_eager(tmp_path):
         solver = Solver(cfg, _solver_args(tmp_path))
         solver.model.load_state_dict(orc.init_state(cfg, seed=0), strict=True)
         solver.trainer.eng.pack_weights(solver.trainer.P, need_dgrad=True)
-        x = torch.randn((4, 80, 128), generator=torch.Generator().manual_seed(1)).cuda()
+        xs = [torch.randn((4, 80, 128), generator=torch.Generator().manual_seed(10 + i)).cuda() for i in range(3)]
+        es = [torch.randn((4, 128, 16), generator=torch.Generator().manual_seed(20 + i)).cuda() for i in range(3)]
         if use_graph:
-            solver.trainer.capture(x, warmup=0)
-        for _ in range(3):
-            solver.trainer.step(x, 1.0)
-        torch.cuda.synchronize()
-        lr_, lk_, gn_ = solver.trainer.losses()
-        assert lr_ > 0 and lk_ > 0 and gn_ > 0
-        outs.append((lr_, lk_))
-    # different eps draws => compare loosely; both must be finite and close
-    assert abs(outs[0][0] - outs[1][0]) / outs[0][0] < 0.05
+            solver.trainer.capture(xs[0], warmup=0, eps_example=es[0])
+        rec = []
+        for i in range(3):
+            solver.trainer.step(xs[i], 1.0, eps=es[i])
+            rec.append(solver.trainer.losses() + (solver.opt.flat_g.detach().cpu().clone(), solver.opt.flat_p.detach().cpu().clone()))
+        if use_graph:
+            assert solver.trainer._graphs is not None
+        outs.append(rec)
+    for (l0, k0, n0, g0, p0), (l1, k1, n1, g1, p1) in zip(*outs):
+        assert abs(l0 - l1) / l0 < 1e-5 and abs(k0 - k1) / k0 < 1e-5 and abs(n0 - n1) / n0 < 1e-4
+        assert rel_l2(g1, g0) < 1e-4, rel_l2(g1, g0)     # same kernels; only atomics / reduction order may differ
+        assert rel_l2(p1, p0) < 1e-5
+
+
+def test_resume_restores_the_annealing_position(tmp_path):
+    """save_model writes <path>.iter next to the reference-format .ckpt/.opt; a new Solver with load_model
+    continues the KL annealing where the first one stopped (the reference restarts it, solver.py:100-104)."""
+    from adaptive_voice_conversion_b200.solver import Solver
+    cfg = orc.default_config(80)
+    cfg["data_loader"]["batch_size"] = 4
+    cfg["annealing_iters"] = 10
+    a = _solver_args(tmp_path)
+    a.save_steps = 3
+    s1 = Solver(cfg, a)
+    lams = []
+    s1.run_steps(3, lambda_of=lambda it: lams.append(it) or 0.1 * (it + 1))
+    assert lams == [0, 1, 2] and s1.iteration == 3
+    s1.save_model(iteration=2)
+    a2 = _solver_args(tmp_path)
+    a2.load_model = True
+    s2 = Solver(cfg, a2)
+    assert s2.iteration == 3
+    lams2 = []
+    s2.run_steps(2, lambda_of=lambda it: lams2.append(it) or 0.1 * (it + 1))
+    assert lams2 == [3, 4]
+    for k, v in s1.model.state_dict().items():      # same weights were loaded before the two extra steps
+        assert v.shape == s2.model.state_dict()[k].shape
+    assert float(s2.opt.step_dev.item()) == 5.0     # Adam's step counter resumed too (3 loaded + 2)
 
 
 def test_inferencer_api(tmp_path, precision):

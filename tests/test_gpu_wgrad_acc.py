@@ -1,6 +1,6 @@
 """GPU: conv weight gradients accumulated in place (vector atomics + one flush launch,
 csrc/wgrad_tc.cu ATOMIC / avc_wgrad_acc_flush) against the two-stage deterministic path and
-against autograd.  Opt-in path, not yet run on a B200: AVC_TEST_EXPERIMENTAL=1 enables the file."""
+against autograd.  Default path since the round-2 B200 validation."""
 import math
 import os
 
@@ -10,8 +10,7 @@ import torch
 import oracle.ae_oracle as orc
 from test_gpu_kernels import relerr, rnd, to_a4
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("AVC_TEST_EXPERIMENTAL") != "1", reason="experimental path: set AVC_TEST_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 TOL = 3e-3
 
 

@@ -78,6 +78,13 @@ def test_bench_reference_arm_schema():
         assert k in d, k
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    # same workload as the product arm's default line: batch 256 per GPU, c_in 80 (not a smaller sample batch)
+    import argparse, importlib.util
+    spec = importlib.util.spec_from_file_location("avc_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    want = bench.workload_config(argparse.Namespace(batch=256, c_in=80), 1)
+    assert {k: d["config"][k] for k in want} == want
 
 
 def test_cli_flags_match_reference_names():
