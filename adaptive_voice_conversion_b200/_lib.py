@@ -118,6 +118,7 @@ PROTOTYPES = {
     "avc_pack_conv_weight_tc": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "avc_tc_packed_floats": (_i64, [_i, _i, _i]),
     "avc_tc_set_debug": (None, [_p]),
+    "avc_tc2_set_debug": (None, [_p]),
     "avc_set_option": (_i, [C.c_char_p, _i]),
     "avc_get_option": (_i, [C.c_char_p]),
     "avc_pack_conv_weights_batch": (_i, [_p, _i, _i64, _p]),
@@ -150,6 +151,7 @@ PROTOTYPES = {
     "avc_adam_step": (_i, [_p, _p, _p, _p, _p, _i64, _p, _p, _p, _p]),
     "avc_fill_zero": (_i, [_p, _i64, _p]),
     "avc_tc_probe_gemm": (_i, [_p, _i, _p, _i, C.POINTER(C.c_uint32), _i, _i, _i, _i, _i, _p, _p, _p]),
+    "avc_tc_probe_set_ld_shift": (None, [_i]),
     "avc_last_error": (C.c_char_p, []),
     "avc_build_info": (C.c_char_p, []),
     "avc_launch_count": (_i64, []),

@@ -22,6 +22,8 @@
 namespace avc {
 
 int validate_conv_desc(const avc_conv_desc* d, const char* who);
+int opt_tc_conv_v2();
+int conv_block_tc2_launch(const avc_conv_desc* d, int* status, void* stream);  // conv_tc2.cu
 
 constexpr int TC_SLAB = 16;          // input channels per pipeline stage (2 MMA K-steps)
 constexpr int TC_WTAP_BYTES = 8192;  // one tap of one slab: 4 chunks x 128 co x 16 B
@@ -612,6 +614,11 @@ extern "C" int avc_conv_block_tc(const avc_conv_desc* d, int* status, void* stre
                 "avc_conv_block_tc: AVC_F_FOLD pads (%d,%d) do not fit %d columns", fpl, fpr, d->Tout);
   }
   AVC_REQUIRE(d->Cin % TC_SLAB == 0, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: Cin %% 16 != 0");
+  AVC_REQUIRE(!d->res || d->res_mode != AVC_RES_NONE, AVC_ERR_INVALID, "avc_conv_block_tc: res without res_mode");
+  if (opt_tc_conv_v2()) {   // persistent kernel (conv_tc2.cu); shapes it does not plan fall through to the round-1 kernel
+    const int rc2 = conv_block_tc2_launch(d, status, stream);
+    if (rc2 != AVC_ERR_UNSUPPORTED) return rc2;
+  }
   const int ncols_full = d->stride == 2 ? 2 * d->Tout - 1 : d->Tout;  // stride 2: full-resolution columns 0 .. 2(Tout-1)
   AVC_REQUIRE(ncols_full <= 256, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: more than 256 columns per sample");
   AVC_REQUIRE(!d->res || d->res_mode != AVC_RES_NONE, AVC_ERR_INVALID, "avc_conv_block_tc: res without res_mode");

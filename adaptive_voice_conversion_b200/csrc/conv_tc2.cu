@@ -1,0 +1,598 @@
+// Fused ConvBlock on the 5th-gen tensor cores, persistent / warp-specialised edition
+// (tcgen05 kind::tf32, fp32 accumulation in TMEM).  Same contract as conv_tc.cu / conv_simt.cu:
+//   reflect|zero pad -> Conv1d -> [pixel shuffle] -> [InstanceNorm] -> [AdaIN] -> [ReLU] -> [+residual] -> [*mask]
+// (model.py:21-32, 52-59, 77-83, 237-250, 309-320, 354-369) and, with the DGRAD weight pack and zero
+// padding, autograd's conv data gradient incl. the adjoint of the reflect padding / residual branch
+// (AVC_F_FOLD).  What changed against conv_tc.cu (round 1), following its own phase counters:
+//
+//   * PERSISTENT CTAs (one per SM) walk a static tile list; a tile = G samples x 128 output channels.
+//   * TWO TMEM ACCUMULATORS (2 x 256 columns): the epilogue of tile i overlaps the main loop of tile
+//     i+1.  Roles: warp 0 bulk-copy (TMA) producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7
+//     halo patch / TF32 rounding of the staged input, warps 8-15 epilogue.  Five mbarrier pipelines:
+//     full / ready / empty per shared-memory stage, acc_full / acc_empty per accumulator.
+//   * STACKED SAMPLES: the G samples of a tile lie one after another in the staged row space at a
+//     pitch of R = (rows one sample needs) and ONE MMA of N <= 256 columns per (k-step, tap) covers all
+//     of them (columns between two samples are garbage and never read): the small-T layers issue
+//     2K MMAs per 16-channel slab instead of 2K*G.
+//   * EPILOGUE THROUGH SHARED MEMORY: one TMEM pass (thread = output channel = TMEM lane) adds the bias,
+//     accumulates the InstanceNorm sums and drops the raw conv row into an A4-layout tile in shared
+//     memory with conflict-free scalar stores (chunk pitch == 1 mod 8 sixteen-byte units); the
+//     accumulator is released right there.  A second pass (thread = one 16-byte A4 unit, lanes along
+//     time) normalises / AdaIN / ReLU / residual / mask / rounds and writes `c` and `out` with fully
+//     coalesced 16-byte stores -- no cross-lane transposes, and the reflect-padding adjoint of the
+//     data-gradient variant becomes three shared-memory reads.
+//   * Halo rows come straight from global memory (no dependence on the bulk copy), so long samples
+//     can be TIME-TILED (T > 144 columns: inference) for blocks without InstanceNorm.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace avc {
+
+int validate_conv_desc(const avc_conv_desc* d, const char* who);
+int opt_tc_conv_v2();
+
+constexpr int T2_SLAB = 16;          // input channels per pipeline stage (2 MMA K-steps)
+constexpr int T2_WTAP_BYTES = 8192;  // one tap of one slab: 4 chunks x 128 co x 16 B
+constexpr int T2_MAX_STAGES = 8;
+constexpr int T2_MAX_G = 8;
+constexpr int T2_SMEM_MAX = 226 * 1024;  // 227 KB per block minus the static shared memory (barriers)
+
+struct Tc2Args {
+  avc_conv_desc d;
+  int G;        // samples per tile
+  int R;        // row pitch between the stacked samples of a tile (= TMEM column pitch)
+  int N;        // MMA N: multiple of 16, <= 256
+  int srows;    // rows of one 4-channel plane of a stage (>= N + K - 1)
+  int nslab, nstage;
+  int TT, ntt;  // output time steps per tile, time tiles per sample
+  int Ts;       // columns one sample stages for the second pass (TT, or Tout for AVC_F_FOLD)
+  int P;        // chunk pitch of the staged tile in 16-byte units (== 1 mod 8)
+  int mtiles, ngroups, ntiles;
+  uint32_t stage_bytes, w_bytes, x_chunk_bytes;
+  uint32_t off_tile, off_par, off_stat;  // byte offsets inside dynamic shared memory
+  int* status;
+  long long* dbg;
+};
+
+__device__ __forceinline__ float t2_round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float4 t2_round4(float4 v) {
+  return make_float4(t2_round_tf32(v.x), t2_round_tf32(v.y), t2_round_tf32(v.z), t2_round_tf32(v.w));
+}
+__device__ __forceinline__ void t2_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+struct TileCoord {
+  int mtile, b0, nsamp, t0, tw;
+};
+__device__ __forceinline__ TileCoord t2_decode(const Tc2Args& a, int tile) {
+  TileCoord c;
+  c.mtile = tile % a.mtiles;
+  const int r = tile / a.mtiles;
+  const int tt = r % a.ntt, grp = r / a.ntt;
+  c.b0 = grp * a.G;
+  c.nsamp = min(a.G, a.d.B - c.b0);
+  c.t0 = tt * a.TT;
+  c.tw = min(a.TT, a.d.Tout - c.t0);
+  return c;
+}
+
+__global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_full[T2_MAX_STAGES], bar_ready[T2_MAX_STAGES], bar_empty[T2_MAX_STAGES], bar_accf[2], bar_acce[2];
+  __shared__ uint32_t tmem_slot;
+  const avc_conv_desc& d = a.d;
+  const int tid = threadIdx.x, warp = tc::warp_idx_sync(), lane = tid & 31;
+  const int K = d.K, S = d.stride;
+
+  if (tid == 0) {
+    for (int s = 0; s < a.nstage; ++s) {
+      tc::mbar_init(&bar_full[s], 1);
+      tc::mbar_init(&bar_ready[s], 128);
+      tc::mbar_init(&bar_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(&bar_accf[b], 1);
+      tc::mbar_init(&bar_acce[b], 256);
+    }
+    tc::fence_mbar_init();
+  }
+  if (warp == 2) tc::tmem_alloc(&tmem_slot, 512u);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  long long tm0 = 0;
+  if (a.dbg && tid == 0) tm0 = clock64();
+
+  if (warp == 0) {
+    // ================================================================ bulk-copy producer
+    int s = 0;
+    uint32_t ph = 0;
+    bool ok = true;
+    bool first_round = true;
+    long long dbg0 = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles && ok; tile += gridDim.x) {
+      const TileCoord c = t2_decode(a, tile);
+      // input positions this tile reads: [t0*S - pad_left, t0*S + (tw-1)*S + K - pad_left); the part inside
+      // [0, Tin) is copied, the rest is written by the patch warps
+      const int pbeg = c.t0 * S - d.pad_left;
+      const int p_lo = max(0, pbeg), p_hi = min(d.Tin, pbeg + (c.tw - 1) * S + K);
+      const int ncopy = max(0, p_hi - p_lo), r_lo = p_lo - pbeg;
+      const float* wsrc = d.w_tc + (size_t)c.mtile * a.nslab * (a.w_bytes / 4);
+      for (int i = 0; i < a.nslab; ++i) {
+        const long long w0 = a.dbg ? clock64() : 0;
+        if (!first_round) ok = __all_sync(0xffffffffu, tc::mbar_wait(&bar_empty[s], ph ^ 1u, a.status, 2));
+        if (a.dbg) dbg0 += clock64() - w0;
+        if (!ok) break;
+        uint8_t* sw = smem + (size_t)s * a.stage_bytes;
+        uint8_t* sx = sw + a.w_bytes;
+        if (tc::elect_one()) {
+          tc::mbar_arrive_expect_tx(&bar_full[s], a.w_bytes + (uint32_t)c.nsamp * 4u * (uint32_t)ncopy * 16u);
+          tc::bulk_g2s(sw, wsrc + (size_t)i * (a.w_bytes / 4), a.w_bytes, &bar_full[s]);
+        }
+        __syncwarp();
+        if (ncopy > 0) {
+          // one copy per (sample, 4-channel plane): lanes issue them in parallel
+          for (int u = lane; u < c.nsamp * 4; u += 32) {
+            const int g = u >> 2, q = u & 3;
+            tc::bulk_g2s(sx + (size_t)q * a.x_chunk_bytes + ((size_t)g * a.R + r_lo) * 16,
+                         d.in + (size_t)(c.b0 + g) * d.in_bstride + ((size_t)(i * 4 + q) * d.Tin + p_lo) * 4, (uint32_t)ncopy * 16u,
+                         &bar_full[s]);
+          }
+        }
+        __syncwarp();
+        if (++s == a.nstage) { s = 0; ph ^= 1u; first_round = false; }
+      }
+    }
+    if (a.dbg && lane == 0) a.dbg[(size_t)blockIdx.x * 16 + 2] = dbg0;
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    // The WHOLE warp runs converged with warp-uniform values and one elected lane executes each tcgen05
+    // instruction (descriptors stay in uniform registers, see conv_tc.cu).
+    const uint32_t idesc = tc::make_idesc_tf32(128, a.N, 0, 0);
+    const uint32_t d_hi = tc::sdesc_hi(128);
+    const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
+    const uint32_t smem0 = tc::smem_u32(smem);
+    const uint32_t ks_b = 2u * (a.x_chunk_bytes >> 4);
+    int s = 0;
+    uint32_t ph = 0;
+    bool ok = true;
+    int tl = 0;
+    long long dbg0 = 0, dbg1 = 0, dbg2 = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles && ok; tile += gridDim.x, ++tl) {
+      const uint32_t buf = (uint32_t)tl & 1u;
+      const long long wa = a.dbg ? clock64() : 0;
+      if (tl >= 2) ok = __all_sync(0xffffffffu, tc::mbar_wait(&bar_acce[buf], (uint32_t)((tl >> 1) - 1) & 1u, a.status, 6));
+      if (a.dbg) dbg1 += clock64() - wa;
+      if (!ok) break;
+      tc::tc_fence_after();
+      const uint32_t dcol = tb + buf * 256u;
+      for (int i = 0; i < a.nslab; ++i) {
+        const long long w0 = a.dbg ? clock64() : 0;
+        ok = __all_sync(0xffffffffu, tc::mbar_wait(&bar_ready[s], ph, a.status, 3));
+        const long long w1 = a.dbg ? clock64() : 0;
+        dbg0 += w1 - w0;
+        if (!ok) break;
+        tc::tc_fence_after();
+        const uint32_t sw = smem0 + (uint32_t)s * a.stage_bytes;
+        const uint32_t a_lo0 = tc::sdesc_lo(sw, 2048), b_lo0 = tc::sdesc_lo(sw + a.w_bytes, a.x_chunk_bytes);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          uint64_t a_desc = tc::sdesc64(a_lo0 + (uint32_t)ks * (4096 >> 4), d_hi);
+          uint64_t b_desc = tc::sdesc64(b_lo0 + (uint32_t)ks * ks_b, d_hi);
+          if (K == 5) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+              tc::mma_tf32_elect(dcol, a_desc, b_desc, idesc, ((uint32_t)i | (uint32_t)ks | (uint32_t)j) ? 1u : 0u);
+              a_desc += (uint64_t)(T2_WTAP_BYTES >> 4);
+              b_desc += 1u;
+            }
+          } else {
+            for (int j = 0; j < K; ++j) {
+              tc::mma_tf32_elect(dcol, a_desc, b_desc, idesc, ((uint32_t)i | (uint32_t)ks | (uint32_t)j) ? 1u : 0u);
+              a_desc += (uint64_t)(T2_WTAP_BYTES >> 4);
+              b_desc += 1u;
+            }
+          }
+        }
+        __syncwarp();
+        if (tc::elect_one()) tc::mma_commit(&bar_empty[s]);
+        __syncwarp();
+        if (a.dbg) dbg2 += clock64() - w1;
+        if (++s == a.nstage) { s = 0; ph ^= 1u; }
+      }
+      if (!ok) break;
+      if (tc::elect_one()) tc::mma_commit(&bar_accf[buf]);
+      __syncwarp();
+    }
+    if (a.dbg && lane == 0) {
+      long long* o = a.dbg + (size_t)blockIdx.x * 16;
+      o[5] = dbg0; o[6] = dbg1; o[7] = dbg2;
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ================================================================ patch warps (128 threads)
+    // rows of the staged tile that are not input data (reflect / zero halo at the ends of a sample) are
+    // written from global memory; data rows are rounded to TF32 in place unless the producer of the
+    // input already rounded them (AVC_F_IN_TF32)
+    const int ptid = tid - 128;
+    const bool rnd = !(d.flags & AVC_F_IN_TF32);
+    int s = 0;
+    uint32_t ph = 0;
+    bool ok = true;
+    long long dbg0 = 0, dbg1 = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles && ok; tile += gridDim.x) {
+      const TileCoord c = t2_decode(a, tile);
+      const int pbeg = c.t0 * S - d.pad_left;
+      const int nr = (c.tw - 1) * S + K;  // rows one sample needs
+      const int p_lo = max(0, pbeg), p_hi = min(d.Tin, pbeg + nr);
+      const int ncopy = max(0, p_hi - p_lo), r_lo = p_lo - pbeg;
+      const int nh = nr - ncopy;
+      for (int i = 0; i < a.nslab && ok; ++i) {
+        const long long w0 = a.dbg ? clock64() : 0;
+        ok = tc::mbar_wait(&bar_full[s], ph, a.status, 4);
+        const long long w1 = a.dbg ? clock64() : 0;
+        dbg0 += w1 - w0;
+        if (!ok) break;
+        float4* sx = reinterpret_cast<float4*>(smem + (size_t)s * a.stage_bytes + a.w_bytes);
+        if (rnd) {
+          for (int r = ptid; r < c.nsamp * ncopy; r += 128) {
+            const int g = r / ncopy, t = r - g * ncopy;
+            float4* p = sx + g * a.R + r_lo + t;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) p[(size_t)q * a.srows] = t2_round4(p[(size_t)q * a.srows]);
+          }
+        }
+        for (int r = ptid; r < c.nsamp * nh; r += 128) {
+          const int g = r / nh, h = r - g * nh;
+          const int u = h < r_lo ? h : h + ncopy;  // row inside the sample's segment
+          const int p = src_pos(pbeg + u, d.Tin, d.pad_mode, 1);
+          const float* src = d.in + (size_t)(c.b0 + g) * d.in_bstride + ((size_t)(i * 4) * d.Tin + (p >= 0 ? p : 0)) * 4;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 v = p >= 0 ? ldg4(src + (size_t)q * d.Tin * 4) : zero4();
+            if (rnd) v = t2_round4(v);
+            sx[(size_t)q * a.srows + g * a.R + u] = v;
+          }
+        }
+        tc::fence_proxy_async_smem();
+        tc::mbar_arrive(&bar_ready[s]);
+        if (a.dbg) dbg1 += clock64() - w1;
+        if (++s == a.nstage) { s = 0; ph ^= 1u; }
+      }
+    }
+    if (a.dbg && ptid == 0) {
+      long long* o = a.dbg + (size_t)blockIdx.x * 16;
+      o[3] = dbg0; o[4] = dbg1;
+    }
+  } else if (warp >= 8) {
+    // ================================================================ epilogue (256 threads)
+    const int etid = tid - 256, ewarp = warp - 8;
+    const int quarter = warp & 3, half = ewarp >> 2;  // TMEM lane quarter of this warp; column half
+    const int col_l = quarter * 32 + lane;            // conv output row inside the 128-row tile
+    float* stile = reinterpret_cast<float*>(smem + a.off_tile);
+    float* par = reinterpret_cast<float*>(smem + a.off_par);          // [3][G][128]: mean, scale, shift
+    float2* stat = reinterpret_cast<float2*>(smem + a.off_stat);      // [2][G][128] partial (sum, sum sq)
+    const int P = a.P, Ts = a.Ts;
+    const int shuf = d.shuffle;
+    const int Cn = shuf ? d.Cout / 2 : d.Cout;
+    const int Tn = shuf ? d.Tout * 2 : d.Tout;                        // normalised length of a whole sample
+    const int out_T = d.out_T > 0 ? d.out_T : Tn;
+    const int ots = d.out_tstride > 0 ? d.out_tstride : 1, oto = d.out_toff;
+    const int sshift = S == 2 ? 1 : 0, smask = sshift;
+    const bool fold = (d.flags & AVC_F_FOLD) != 0;
+    const int fpl = (d.flags >> 8) & 0xff, fpr = (d.flags >> 16) & 0xff;
+    const bool rnd_out = (d.flags & AVC_F_ROUND_OUT) != 0;
+    bool ok = true;
+    int tl = 0;
+    long long dbg0 = 0, dbg1 = 0, dbg2 = 0, dbg3 = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tl) {
+      const TileCoord c = t2_decode(a, tile);
+      const uint32_t buf = (uint32_t)tl & 1u;
+      const long long e0 = a.dbg ? clock64() : 0;
+      ok = tc::mbar_wait(&bar_accf[buf], (uint32_t)(tl >> 1) & 1u, a.status, 5) && ok;
+      tc::tc_fence_after();
+      const long long e1 = a.dbg ? clock64() : 0;
+      const int co = c.mtile * 128 + col_l;
+      const bool co_ok = co < d.Cout;
+      const float bias = (d.bias && co_ok) ? __ldg(d.bias + co) : 0.f;
+      const int ncol = (c.tw - 1) * S + 1;  // TMEM columns of one sample that hold outputs
+      const int nch = (ncol + 15) >> 4;
+      const uint32_t lane_addr = tbase + ((uint32_t)(quarter * 32) << 16) + buf * 256u;
+      // ---------------- pass 0: TMEM -> (+bias, InstanceNorm sums) -> staged A4 tile
+      if (ok) {
+        float* srow = stile + ((size_t)(col_l >> 2) * P) * 4 + (col_l & 3);
+        for (int g = 0; g < c.nsamp; ++g) {
+          float s1 = 0.f, s2 = 0.f;
+          float* sdst = srow + (size_t)(g * Ts) * 4;
+          for (int j = half; j < nch; j += 2) {
+            float v[16];
+            tc::tmem_ld16(lane_addr + (uint32_t)(g * a.R + 16 * j), v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int col = 16 * j + i;
+              if (col < ncol && (col & smask) == 0) {
+                const float x = v[i] + bias;
+                s1 += x;
+                s2 = fmaf(x, x, s2);
+                sdst[(size_t)(col >> sshift) * 4] = x;
+              }
+            }
+          }
+          if (d.norm) stat[(half * a.G + g) * 128 + col_l] = make_float2(s1, s2);
+        }
+      }
+      tc::tc_fence_before();
+      tc::mbar_arrive(&bar_acce[buf]);  // the accumulator is free: the MMA warp may start tile tl+2 into it
+      const long long e2 = a.dbg ? clock64() : 0;
+      t2_bar_sync(2, 256);
+      // ---------------- per (sample, channel) parameters: mean, scale = rstd*gamma, shift = beta
+      for (int g = half; g < c.nsamp; g += 2) {
+        const int b = c.b0 + g;
+        float mean = 0.f, rstd = 1.f;
+        const int cn = shuf ? co >> 1 : co;
+        if (d.norm) {
+          const float2 p0 = stat[(0 * a.G + g) * 128 + col_l], p1 = stat[(1 * a.G + g) * 128 + col_l];
+          float s1 = p0.x + p1.x, s2 = p0.y + p1.y;
+          if (shuf) {  // conv rows (2c, 2c+1) pool into normalised channel c
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+          }
+          const float inv = 1.f / (float)Tn;
+          mean = s1 * inv;
+          const float var = fmaxf(s2 * inv - mean * mean, 0.f);
+          rstd = rsqrtf(var + d.eps);
+          if (d.stats && co_ok && (!shuf || (co & 1) == 0)) {
+            d.stats[((size_t)b * Cn + cn) * 2 + 0] = mean;
+            d.stats[((size_t)b * Cn + cn) * 2 + 1] = rstd;
+          }
+        }
+        float beta = 0.f, gamma = 1.f;
+        if (d.cond && co_ok) {
+          beta = __ldg(d.cond + (size_t)b * d.cond_bstride + cn);
+          gamma = __ldg(d.cond + (size_t)b * d.cond_bstride + Cn + cn);
+        }
+        par[(0 * a.G + g) * 128 + col_l] = mean;
+        par[(1 * a.G + g) * 128 + col_l] = rstd * gamma;
+        par[(2 * a.G + g) * 128 + col_l] = beta;
+      }
+      t2_bar_sync(2, 256);
+      const long long e3 = a.dbg ? clock64() : 0;
+      // ---------------- pass B: staged tile -> c / out, thread = one 16-byte A4 unit, lanes along time
+      if (ok) {
+        const int nq = min(32, (d.Cout - c.mtile * 128) >> 2);  // valid 4-row chunks of this tile
+        const float4* st4p = reinterpret_cast<const float4*>(stile);
+        const float4* par4 = reinterpret_cast<const float4*>(par);
+        if (fold) {
+          // D holds Tout = T + pl + pr columns of the zero-padded transposed conv; dx[t] = D[t+pl]
+          // + D[pl-t] (1 <= t <= pl) + D[2(T-1)-t+pl] (t >= T-1-pr, t <= T-2) + residual adjoint
+          const int Tf = d.Tout - fpl - fpr;
+          for (int row = ewarp; row < c.nsamp * nq; row += 8) {
+            const int g = row / nq, cql = row - g * nq;
+            const int b = c.b0 + g, cq = c.mtile * 32 + cql;
+            const float4* sr = st4p + (size_t)cql * P + g * Ts;
+            float* ob = d.out + (size_t)b * d.out_bstride + ((size_t)cq * Tf) * 4;
+            const float* rb = d.res ? d.res + (size_t)b * d.res_bstride + ((size_t)cq * d.res_T) * 4 : nullptr;
+            for (int t = lane; t < Tf; t += 32) {
+              float4 o = sr[t + fpl];
+              if (t >= 1 && t <= fpl) {
+                const float4 m = sr[fpl - t];
+                o.x += m.x; o.y += m.y; o.z += m.z; o.w += m.w;
+              }
+              if (t <= Tf - 2 && t >= Tf - 1 - fpr) {
+                const float4 m = sr[2 * (Tf - 1) - t + fpl];
+                o.x += m.x; o.y += m.y; o.z += m.z; o.w += m.w;
+              }
+              if (rb) {  // adjoint of the forward residual branch (same cases as fold_add_kernel)
+                float4 r;
+                if (d.res_mode == AVC_RES_SAME) {
+                  r = ldg4(rb + (size_t)t * 4);
+                } else if (d.res_mode == AVC_RES_POOL) {
+                  r = ldg4(rb + (size_t)(t >> 1) * 4);
+                  const float wgt = ((Tf & 1) && t == Tf - 1) ? 1.f : 0.5f;
+                  r.x *= wgt; r.y *= wgt; r.z *= wgt; r.w *= wgt;
+                } else {
+                  r = ldg4(rb + (size_t)(2 * t) * 4);
+                  const float4 r2 = ldg4(rb + (size_t)(2 * t + 1) * 4);
+                  r.x += r2.x; r.y += r2.y; r.z += r2.z; r.w += r2.w;
+                }
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+              }
+              st4(ob + (size_t)t * 4, o);
+            }
+          }
+        } else {
+          if (d.save_c) {  // raw conv (+bias) rows in conv layout, kept for the backward pass
+            for (int row = ewarp; row < c.nsamp * nq; row += 8) {
+              const int g = row / nq, cql = row - g * nq;
+              const float4* sr = st4p + (size_t)cql * P + g * Ts;
+              float* cb = d.save_c + (((size_t)(c.b0 + g) * (d.Cout >> 2) + (c.mtile * 32 + cql)) * d.Tout + c.t0) * 4;
+              for (int t = lane; t < c.tw; t += 32) st4(cb + (size_t)t * 4, sr[t]);
+            }
+          }
+          const int nqo = shuf ? nq >> 1 : nq;       // output chunks of this tile
+          const int two = shuf ? c.tw * 2 : c.tw;    // output time steps of this tile
+          const int to0 = shuf ? c.t0 * 2 : c.t0;    // first output time step of this tile
+          for (int row = ewarp; row < c.nsamp * nqo; row += 8) {
+            const int g = row / nqo, cql = row - g * nqo;
+            const int b = c.b0 + g;
+            const int cqo = c.mtile * (shuf ? 16 : 32) + cql;
+            float* ob = d.out + (size_t)b * d.out_bstride + ((size_t)cqo * out_T) * 4;
+            const float* rb = d.res ? d.res + (size_t)b * d.res_bstride + ((size_t)cqo * d.res_T) * 4 : nullptr;
+            const float* mb = d.mask ? d.mask + (size_t)b * d.mask_bstride + ((size_t)cqo * Tn) * 4 : nullptr;
+            float4 mean4, sc4, sh4;
+            const float4 *srA, *srB = nullptr;
+            if (!shuf) {
+              mean4 = par4[(0 * a.G + g) * 32 + cql];
+              sc4 = par4[(1 * a.G + g) * 32 + cql];
+              sh4 = par4[(2 * a.G + g) * 32 + cql];
+              srA = st4p + (size_t)cql * P + g * Ts;
+            } else {
+              // output channel 4*cql+j <- conv row 8*cql + 2j + s (s = output time parity): rows of the
+              // conv chunks 2*cql (j = 0, 1) and 2*cql+1 (j = 2, 3); the parameters of a row pair are equal
+              const float4 mA = par4[(0 * a.G + g) * 32 + 2 * cql], mB = par4[(0 * a.G + g) * 32 + 2 * cql + 1];
+              const float4 cA = par4[(1 * a.G + g) * 32 + 2 * cql], cB = par4[(1 * a.G + g) * 32 + 2 * cql + 1];
+              const float4 hA = par4[(2 * a.G + g) * 32 + 2 * cql], hB = par4[(2 * a.G + g) * 32 + 2 * cql + 1];
+              mean4 = make_float4(mA.x, mA.z, mB.x, mB.z);
+              sc4 = make_float4(cA.x, cA.z, cB.x, cB.z);
+              sh4 = make_float4(hA.x, hA.z, hB.x, hB.z);
+              srA = st4p + (size_t)(2 * cql) * P + g * Ts;
+              srB = st4p + (size_t)(2 * cql + 1) * P + g * Ts;
+            }
+            for (int tl_ = lane; tl_ < two; tl_ += 32) {
+              float4 x;
+              if (!shuf) {
+                x = srA[tl_];
+              } else {
+                const float4 va = srA[tl_ >> 1], vb = srB[tl_ >> 1];
+                x = (tl_ & 1) ? make_float4(va.y, va.w, vb.y, vb.w) : make_float4(va.x, va.z, vb.x, vb.z);
+              }
+              const int t = to0 + tl_;  // output time step inside the sample
+              float4 o;
+              o.x = fmaf(x.x - mean4.x, sc4.x, sh4.x); o.y = fmaf(x.y - mean4.y, sc4.y, sh4.y);
+              o.z = fmaf(x.z - mean4.z, sc4.z, sh4.z); o.w = fmaf(x.w - mean4.w, sc4.w, sh4.w);
+              if (d.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              if (rb) {
+                float4 r;
+                if (d.res_mode == AVC_RES_SAME) r = ldg4(rb + (size_t)t * 4);
+                else if (d.res_mode == AVC_RES_UP) r = ldg4(rb + (size_t)(t >> 1) * 4);
+                else {
+                  r = ldg4(rb + (size_t)(2 * t) * 4);
+                  if (2 * t + 1 < d.res_T) {
+                    const float4 r2 = ldg4(rb + (size_t)(2 * t + 1) * 4);
+                    r.x = 0.5f * (r.x + r2.x); r.y = 0.5f * (r.y + r2.y); r.z = 0.5f * (r.z + r2.z); r.w = 0.5f * (r.w + r2.w);
+                  }
+                }
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+              }
+              if (mb) {
+                const float4 m = ldg4(mb + (size_t)t * 4);
+                o.x = m.x > 0.f ? o.x : 0.f; o.y = m.y > 0.f ? o.y : 0.f; o.z = m.z > 0.f ? o.z : 0.f; o.w = m.w > 0.f ? o.w : 0.f;
+              }
+              if (rnd_out) o = t2_round4(o);
+              st4(ob + (size_t)(t * ots + oto) * 4, o);
+            }
+          }
+        }
+      }
+      t2_bar_sync(2, 256);  // the staged tile and the parameter arrays are reused by the next tile
+      if (a.dbg) {
+        const long long e4 = clock64();
+        dbg0 += e1 - e0; dbg1 += e2 - e1; dbg2 += e3 - e2; dbg3 += e4 - e3;
+      }
+    }
+    if (a.dbg && etid == 0) {
+      long long* o = a.dbg + (size_t)blockIdx.x * 16;
+      o[8] = dbg0; o[9] = dbg1; o[10] = dbg2; o[11] = dbg3; o[12] = tl;
+    }
+  }
+  if (a.dbg && tid == 0) {
+    long long* o = a.dbg + (size_t)blockIdx.x * 16;
+    o[0] = tm0; o[1] = clock64();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tbase, 512u);
+}
+
+// ------------------------------------------------------------------ host side: tile plan
+static int t2_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaDeviceProp p;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&p, dev) == cudaSuccess) n = p.multiProcessorCount;
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// returns AVC_OK and fills a, or AVC_ERR_UNSUPPORTED (caller falls back to the round-1 kernel / FFMA path)
+int t2_plan(const avc_conv_desc* d, Tc2Args& a) {
+  const int K = d->K, S = d->stride;
+  const bool fold = (d->flags & AVC_F_FOLD) != 0;
+  a.d = *d;
+  if (!a.d.res) a.d.res_mode = AVC_RES_NONE;
+  a.nslab = d->Cin / T2_SLAB;
+  a.w_bytes = (uint32_t)K * T2_WTAP_BYTES;
+  a.mtiles = cdiv(d->Cout, 128);
+  const int ncol_full = (d->Tout - 1) * S + 1;
+  if (ncol_full <= 144) {
+    a.TT = d->Tout;
+    a.ntt = 1;
+  } else {
+    if (d->norm || fold || d->shuffle) return AVC_ERR_UNSUPPORTED;  // whole-sample statistics / fold need one tile per sample
+    a.TT = S == 2 ? 64 : 128;
+    a.ntt = cdiv(d->Tout, a.TT);
+  }
+  a.Ts = a.TT;  // fold: TT == Tout (all columns incl. the halo ones are staged)
+  const int ncol = (a.TT - 1) * S + 1;
+  a.R = ncol + K - 1;
+  // samples per tile: minimise rounds x (fixed + MMA time); an N-column MMA costs ~max(40, N/2) cycles
+  const int sms = t2_num_sms();
+  int bestG = 0;
+  double best = 1e30;
+  const int gmax = a.ntt > 1 ? 1 : T2_MAX_G;
+  for (int G = 1; G <= gmax && G <= d->B; ++G) {
+    if (G * a.Ts > 144) break;
+    const int span = (G - 1) * a.R;
+    if (span + (ncol + 15) / 16 * 16 > 256) break;
+    const int N = (span + ncol + 15) / 16 * 16;
+    const int ntiles = cdiv(d->B, G) * a.ntt * a.mtiles;
+    const double mma = (double)a.nslab * 2 * K * (N / 2 > 40 ? N / 2 : 40);
+    const double cost = (double)cdiv(ntiles, sms) * (3000.0 + mma);
+    if (cost <= best) { best = cost; bestG = G; }
+  }
+  if (bestG == 0) return AVC_ERR_UNSUPPORTED;
+  a.G = bestG;
+  a.N = ((a.G - 1) * a.R + ncol + 15) / 16 * 16;
+  a.srows = (a.N + K - 1 + 7) / 8 * 8;
+  a.x_chunk_bytes = (uint32_t)a.srows * 16u;
+  a.stage_bytes = (a.w_bytes + 4u * a.x_chunk_bytes + 1023u) / 1024u * 1024u;
+  a.ngroups = cdiv(d->B, a.G);
+  a.ntiles = a.ngroups * a.ntt * a.mtiles;
+  // staged tile: 32 chunks, pitch == 1 mod 8 sixteen-byte units
+  const int cols = a.G * a.Ts;
+  a.P = (cols + 7) / 8 * 8 + 1;
+  const uint32_t tile_bytes = 32u * (uint32_t)a.P * 16u;
+  const uint32_t par_bytes = 3u * (uint32_t)a.G * 128u * 4u, stat_bytes = 2u * (uint32_t)a.G * 128u * 8u;
+  const uint32_t tail = tile_bytes + par_bytes + stat_bytes;
+  int nstage = (int)((T2_SMEM_MAX - (int)tail) / (int)a.stage_bytes);
+  if (nstage > T2_MAX_STAGES) nstage = T2_MAX_STAGES;
+  if (nstage < 2) return AVC_ERR_UNSUPPORTED;
+  a.nstage = nstage;
+  a.off_tile = (uint32_t)nstage * a.stage_bytes;
+  a.off_par = a.off_tile + tile_bytes;
+  a.off_stat = a.off_par + par_bytes;
+  return AVC_OK;
+}
+
+static long long* g_tc2_dbg = nullptr;
+
+int conv_block_tc2_launch(const avc_conv_desc* d, int* status, void* stream) {
+  Tc2Args a;
+  const int rc = t2_plan(d, a);
+  if (rc != AVC_OK) return rc;
+  a.status = status;
+  a.dbg = g_tc2_dbg;
+  const int smem = (int)(a.off_stat + 2u * (uint32_t)a.G * 128u * 8u);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_block_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_MAX);
+    if (e != cudaSuccess) {
+      set_error("avc_conv_block_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return AVC_ERR_CUDA;
+    }
+    attr_done = true;
+  }
+  const int grid = a.ntiles < t2_num_sms() ? a.ntiles : t2_num_sms();
+  AVC_LAUNCH(conv_block_tc2_kernel, grid, 512, smem, (cudaStream_t)stream, a);
+  AVC_CHECK_LAUNCH("conv_block_tc2");
+  return AVC_OK;
+}
+
+}  // namespace avc
+
+extern "C" void avc_tc2_set_debug(void* dev_buffer) { avc::g_tc2_dbg = (long long*)dev_buffer; }

@@ -12,7 +12,7 @@ struct ProbeArgs {
   const float* b_img;
   int a_bytes, b_bytes;
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo, a_kstep, b_kstep, a_off, b_off, a_layout, b_layout;
-  int nk, N, reps;
+  int nk, N, reps, ld_shift;
   uint32_t idesc;
   float* D;
   int* status;
@@ -54,12 +54,16 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const ProbeArgs a) {
   if (tid == 0) a.status[1] = (int)(clock64() - t0);  // cycles: issue of the first MMA -> all complete
   tc::tc_fence_after();
   if (ok) {
-    for (int c0 = 0; c0 < a.N; c0 += 16) {
+    // ld_shift != 0: the 16-column loads start at column ld_shift + 16 j (NOT a multiple of 16) -- pins that
+    // tcgen05.ld accepts any start column (the conv epilogue reads samples stacked at an arbitrary pitch)
+    const int sh = a.ld_shift;
+    for (int c0 = 0; c0 + sh + 16 <= (int)ncols || c0 == 0; c0 += 16) {
+      if (c0 + sh >= a.N) break;
       float v[16];
-      tc::tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + c0, v);
+      tc::tmem_ld16(tbase + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c0 + sh), v);
 #pragma unroll
       for (int i = 0; i < 16; ++i)
-        if (c0 + i < a.N) a.D[(size_t)tid * a.N + c0 + i] = v[i];
+        if (c0 + sh + i < a.N) a.D[(size_t)tid * a.N + c0 + sh + i] = v[i];
     }
   }
   tc::tc_fence_before();
@@ -71,6 +75,9 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const ProbeArgs a) {
 
 using namespace avc;
 
+static int g_probe_ld_shift = 0;
+extern "C" void avc_tc_probe_set_ld_shift(int shift) { g_probe_ld_shift = shift < 0 ? 0 : shift; }
+
 extern "C" int avc_tc_probe_gemm(const float* a_img, int a_bytes, const float* b_img, int b_bytes, const uint32_t* strides /*[10]*/,
                                  int nk, int N, int a_mn, int b_mn, int reps, float* D, int* status, void* stream) {
   AVC_REQUIRE(a_img && b_img && strides && D && status, AVC_ERR_INVALID, "avc_tc_probe_gemm: null argument");
@@ -81,7 +88,7 @@ extern "C" int avc_tc_probe_gemm(const float* a_img, int a_bytes, const float* b
   a.a_lbo = strides[0]; a.a_sbo = strides[1]; a.b_lbo = strides[2]; a.b_sbo = strides[3];
   a.a_kstep = strides[4]; a.b_kstep = strides[5]; a.a_off = strides[6]; a.b_off = strides[7];
   a.a_layout = strides[8]; a.b_layout = strides[9];
-  a.nk = nk; a.N = N; a.reps = reps < 1 ? 1 : reps; a.idesc = tc::make_idesc_tf32(128, N, a_mn, b_mn); a.D = D; a.status = status;
+  a.nk = nk; a.N = N; a.reps = reps < 1 ? 1 : reps; a.ld_shift = g_probe_ld_shift; a.idesc = tc::make_idesc_tf32(128, N, a_mn, b_mn); a.D = D; a.status = status;
   const int smem = ((a_bytes + 1023) / 1024) * 1024 + b_bytes + 1024;
   AVC_REQUIRE(smem <= 200 * 1024, AVC_ERR_INVALID, "avc_tc_probe_gemm: images too large");
   cudaError_t e = cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -105,6 +105,7 @@ class Engine:
         # epilogue (AVC_F_FOLD) instead of a separate avc_fold_add_fwd pass
         self.fold_fused = os.environ.get("AVC_FOLD_FUSED", "1" if L.DEFAULT_FOLD_FUSED else "0") == "1"
         self._wg_acc = None
+        self.tc_conv_v2 = bool(self.lib.avc_get_option(b"tc_conv_v2"))
 
     # ------------------------------------------------------------------ utilities
     @property
@@ -291,8 +292,10 @@ class Engine:
             out = A4.empty(B, Cn, Tn, self.dev)
         assert (out.C, out.T) == (Cn, Tn)
         need_c = train and (norm or relu)
-        use_tc = (self.precision == "tf32" and Cin % 16 == 0 and Tout * stride <= 256 and not (stride == 2 and shuffle)
-                  and "fwd_tc" in self.packed[name])
+        # tcgen05 path: one tile per sample up to 256 columns; longer samples are time-tiled by the persistent
+        # kernel when the block has no whole-sample statistics (no InstanceNorm / pixel shuffle)
+        use_tc = (self.precision == "tf32" and Cin % 16 == 0 and not (stride == 2 and shuffle) and "fwd_tc" in self.packed[name]
+                  and (Tout * stride <= 256 or (self.tc_conv_v2 and not norm and not shuffle)))
         fused = use_tc or (not norm) or (Tout <= 128) or (Tout <= 256 and K in (1, 5))
         c = A4.empty(B, Cout, Tout, self.dev) if (need_c or not fused) else None
         stats = self.empty(B, Cn, 2) if norm else None

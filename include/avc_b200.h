@@ -122,9 +122,14 @@ int64_t avc_tc_packed_floats(int co_total, int ci_total, int K);
 /* Diagnostics: device buffer of 4 int64 per CTA receiving clock64 at kernel start / main loop
  * done / epilogue done for subsequent avc_conv_block_tc launches (null disables). */
 void avc_tc_set_debug(void* dev_buffer);
+/* Same for the persistent kernel: 16 int64 per CTA: [0] start [1] end clock; wait / work cycle sums of the roles:
+ * [2] producer wait-empty, [3] patch wait-full [4] patch work, [5] MMA wait-ready [6] wait-accumulator [7] issue,
+ * [8] epilogue wait-accumulator [9] TMEM pass [10] parameters [11] store pass, [12] tiles done. */
+void avc_tc2_set_debug(void* dev_buffer);
 /* Runtime options (process-wide; each also has an environment default read on first use):
  *   "tc_uniform_issue"  (AVC_TC_ISSUE=uniform|legacy)   tcgen05 issue loops on the uniform datapath
  *   "wgrad_reduce_v2"   (AVC_WGRAD_REDUCE=v2|v1)        unrolled partial-sum reduction of conv_wgrad_tc
+ *   "tc_conv_v2"        (AVC_TC_CONV=v2|v1)             persistent, epilogue-overlapped conv block kernel (default on)
  * avc_set_option returns AVC_ERR_INVALID for an unknown name; avc_get_option returns -1. */
 int avc_set_option(const char* name, int value);
 int avc_get_option(const char* name);
@@ -315,6 +320,9 @@ int avc_fill_zero(void* ptr, int64_t bytes, void* stream);
  * pin the UMMA descriptor conventions the conv kernels rely on. */
 int avc_tc_probe_gemm(const float* a_img, int a_bytes, const float* b_img, int b_bytes, const uint32_t* strides,
                       int nk, int N, int a_mn, int b_mn, int reps, float* D, int* status, void* stream);
+/* Read-back variant of the self-test: the accumulator is read with 16-column tcgen05.ld's starting at
+ * column `shift` + 16 j (any shift >= 0; columns below `shift` are left untouched in D). */
+void avc_tc_probe_set_ld_shift(int shift);
 
 const char* avc_last_error(void);
 /* "sm_100a" build tag, number of kernels launched so far by this process (for bench.py's

@@ -5,6 +5,11 @@ that hold whatever the batch size and need no CPU-sized oracle run --
   * homogeneity of the gradient in (lambda_rec, lambda_kl),
   * data-parallel semantics: the gradient of the whole batch is the mean of the gradients of its
     two halves (what the NCCL all-reduce + 1/world scale computes).
+Both arithmetic modes.  In tf32 mode activations that feed a tensor-core conv are ROUNDED to a 10-bit mantissa:
+rounding is discontinuous, so a 1e-7 difference in an InstanceNorm sum (another summation order for another
+tile shape) is amplified layer by layer up to the TF32 noise floor (~5e-4) -- exactly as far as either result is
+from the fp32 reference.  Measured in round 2 (tools/diag_batchdep.py): every kernel is bit-identical or 1e-7
+apart per sample across batch sizes, the 14-layer content encoder 5e-4.  Tolerances below reflect that.
 """
 import os
 import types
@@ -24,9 +29,12 @@ def rel_l2(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-@pytest.fixture(scope="module")
-def rig(tmp_path_factory):
+@pytest.fixture(scope="module", params=["fp32", "tf32"])
+def rig(request, tmp_path_factory):
     from adaptive_voice_conversion_b200.solver import Solver
+    mp = pytest.MonkeyPatch()
+    mp.setenv("AVC_PRECISION", request.param)
+    request.addfinalizer(mp.undo)
     tmp = tmp_path_factory.mktemp("prop")
     cfg = orc.default_config(C_IN)
     cfg["data_loader"]["batch_size"] = B
@@ -39,7 +47,12 @@ def rig(tmp_path_factory):
     g = torch.Generator().manual_seed(1)
     x = torch.randn((B, C_IN, T), generator=g).cuda()
     eps = torch.randn((B, 128, T // 8), generator=g).cuda()
+    assert solver.trainer.eng.precision == request.param
     return solver, x, eps
+
+
+def tol(solver, fp32, tf32):
+    return fp32 if solver.trainer.eng.precision == "fp32" else tf32
 
 
 def grad_of(solver, x, eps, lambda_rec=10.0, lambda_kl=1.0):
@@ -68,7 +81,7 @@ def test_gradient_is_permutation_invariant(rig):
     g0, _ = grad_of(solver, x, eps)
     perm = torch.randperm(B, generator=torch.Generator().manual_seed(7)).cuda()
     g1, _ = grad_of(solver, x[perm], eps[perm])
-    assert rel_l2(g1, g0) < 1e-4, rel_l2(g1, g0)      # same terms, different summation order
+    assert rel_l2(g1, g0) < tol(solver, 1e-4, 2e-2), rel_l2(g1, g0)      # same terms, different summation order
 
 
 def test_gradient_is_homogeneous_in_the_loss_weights(rig):
@@ -85,4 +98,4 @@ def test_whole_batch_gradient_is_the_mean_of_the_half_batch_gradients(rig):
     h = B // 2
     ga, _ = grad_of(solver, x[:h], eps[:h])
     gb, _ = grad_of(solver, x[h:], eps[h:])
-    assert rel_l2(0.5 * (ga + gb), g) < 1e-4, rel_l2(0.5 * (ga + gb), g)
+    assert rel_l2(0.5 * (ga + gb), g) < tol(solver, 1e-4, 2e-2), rel_l2(0.5 * (ga + gb), g)

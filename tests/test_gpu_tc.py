@@ -75,3 +75,24 @@ def test_mn_major_gemm():
     strides = [128, Kt * 16, 128, Kt * 16, 128, 128, 0, 0]
     D = run_probe(a_img, b_img, strides, Kt // 8, N, a_mn=1, b_mn=1)
     assert rel(D, At.t() @ Bt) < 2e-3, rel(D, At.t() @ Bt)
+
+
+@pytest.mark.parametrize("shift", [1, 4, 20, 36, 132])
+def test_tmem_load_at_any_start_column(shift):
+    """tcgen05.ld 32x32b.x16 accepts a start column that is not a multiple of 16: the persistent conv kernel
+    stacks samples in TMEM at a pitch of T+K-1 columns and reads every sample from its own first column."""
+    from adaptive_voice_conversion_b200 import _lib as L
+    N, K = 256, 16
+    g = torch.Generator().manual_seed(shift)
+    A, B = torch.randn((128, K), generator=g), torch.randn((N, K), generator=g)
+    strides = [128 * 16, 128, N * 16, 128, 2 * 128 * 16, 2 * N * 16, 0, 0]
+    lib = L.load()
+    lib.avc_tc_probe_set_ld_shift(shift)
+    try:
+        D = run_probe(img_kmajor(A), img_kmajor(B), strides, K // 8, N)
+    finally:
+        lib.avc_tc_probe_set_ld_shift(0)
+    ref = A @ B.t()
+    hi = shift + ((N - shift) // 16) * 16                       # whole 16-column loads that fit in the allocation
+    assert torch.isnan(D[:, :shift]).all()                      # untouched
+    assert rel(D[:, shift:hi], ref[:, shift:hi]) < 2e-3, rel(D[:, shift:hi], ref[:, shift:hi])

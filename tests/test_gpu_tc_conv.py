@@ -37,8 +37,16 @@ CASES = [
     (2, 128, 128, 5, 37, 0, 1, 0, 1, 1),      # odd length
     (2, 128, 128, 5, 200, 0, 1, 0, 1, 1),     # N = 208 columns
     (2, 128, 128, 5, 256, 0, 1, 1, 1, 1),
+    # persistent kernel (conv_tc2.cu): more tiles than SMs (both TMEM accumulators, barrier phases wrap)
+    (301, 128, 128, 5, 128, 0, 1, 0, 1, 1),
+    (601, 128, 128, 5, 64, 0, 1, 1, 1, 1),    # 2 samples per tile, odd tail
+    (450, 128, 256, 5, 32, 1, 1, 1, 1, 3),    # stacked samples + pixel shuffle, two M tiles
+    (3, 128, 128, 5, 512, 0, 0, 0, 1, 1),     # time-tiled long sample (no InstanceNorm): 4 tiles of 128 columns
+    (2, 128, 128, 5, 300, 0, 0, 0, 1, 0),     # ragged last time tile
+    (2, 80, 128, 8, 333, 0, 0, 0, 1, 0),      # even kernel, time-tiled
 ]
-CASES_S2 = [(5, 128, 128, 5, 128, 1), (19, 128, 128, 5, 32, 0), (3, 128, 128, 5, 37, 1), (300, 128, 128, 5, 64, 1)]
+CASES_S2 = [(5, 128, 128, 5, 128, 1), (19, 128, 128, 5, 32, 0), (3, 128, 128, 5, 37, 1), (300, 128, 128, 5, 64, 1), (333, 128, 128, 5, 128, 1),
+            (3, 128, 128, 5, 512, 0)]
 
 
 @pytest.mark.parametrize("B,Cin,Cout,K,T,norm", CASES_S2)
