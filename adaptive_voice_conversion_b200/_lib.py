@@ -119,6 +119,8 @@ PROTOTYPES = {
     "avc_tc_packed_floats": (_i64, [_i, _i, _i]),
     "avc_tc_set_debug": (None, [_p]),
     "avc_tc2_set_debug": (None, [_p]),
+    "avc_tc2_set_variant": (None, [_i]),
+    "avc_wgrad_tc_set_debug": (None, [_p]),
     "avc_set_option": (_i, [C.c_char_p, _i]),
     "avc_get_option": (_i, [C.c_char_p]),
     "avc_pack_conv_weights_batch": (_i, [_p, _i, _i64, _p]),

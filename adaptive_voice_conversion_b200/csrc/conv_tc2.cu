@@ -23,6 +23,9 @@
 //     data-gradient variant becomes three shared-memory reads.
 //   * Halo rows come straight from global memory (no dependence on the bulk copy), so long samples
 //     can be TIME-TILED (T > 144 columns: inference) for blocks without InstanceNorm.
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -50,6 +53,8 @@ struct Tc2Args {
   int mtiles, ngroups, ntiles;
   uint32_t stage_bytes, w_bytes, x_chunk_bytes;
   uint32_t off_tile, off_par, off_stat;  // byte offsets inside dynamic shared memory
+  int patch;    // 1: the patch warps sit between the bulk copy and the MMAs (halo rows and/or TF32 rounding)
+  int variant;  // bit 0: `c` rows leave through bulk (TMA) stores; bit 1: `out` rows too (written back in place)
   int* status;
   long long* dbg;
 };
@@ -79,7 +84,10 @@ __device__ __forceinline__ TileCoord t2_decode(const Tc2Args& a, int tile) {
   return c;
 }
 
-__global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a) {
+// tmx: 4-D tensor map of the input, dims (4 floats, time, sample, 4-channel chunk): ONE copy-engine instruction
+// stages [4 chunks][G samples][R rows] of a 16-channel slab -- exactly the stacked-sample operand layout -- and
+// rows / samples outside the tensor arrive as zeros (that IS the zero padding of the data-gradient convs).
+__global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a, const __grid_constant__ CUtensorMap tmx) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_full[T2_MAX_STAGES], bar_ready[T2_MAX_STAGES], bar_empty[T2_MAX_STAGES], bar_accf[2], bar_acce[2];
   __shared__ uint32_t tmem_slot;
@@ -116,32 +124,18 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a)
     long long dbg0 = 0;
     for (int tile = blockIdx.x; tile < a.ntiles && ok; tile += gridDim.x) {
       const TileCoord c = t2_decode(a, tile);
-      // input positions this tile reads: [t0*S - pad_left, t0*S + (tw-1)*S + K - pad_left); the part inside
-      // [0, Tin) is copied, the rest is written by the patch warps
-      const int pbeg = c.t0 * S - d.pad_left;
-      const int p_lo = max(0, pbeg), p_hi = min(d.Tin, pbeg + (c.tw - 1) * S + K);
-      const int ncopy = max(0, p_hi - p_lo), r_lo = p_lo - pbeg;
       const float* wsrc = d.w_tc + (size_t)c.mtile * a.nslab * (a.w_bytes / 4);
+      const int tstart = c.t0 * S - d.pad_left;   // first input position of the staged rows (may be negative)
       for (int i = 0; i < a.nslab; ++i) {
         const long long w0 = a.dbg ? clock64() : 0;
         if (!first_round) ok = __all_sync(0xffffffffu, tc::mbar_wait(&bar_empty[s], ph ^ 1u, a.status, 2));
         if (a.dbg) dbg0 += clock64() - w0;
         if (!ok) break;
         uint8_t* sw = smem + (size_t)s * a.stage_bytes;
-        uint8_t* sx = sw + a.w_bytes;
         if (tc::elect_one()) {
-          tc::mbar_arrive_expect_tx(&bar_full[s], a.w_bytes + (uint32_t)c.nsamp * 4u * (uint32_t)ncopy * 16u);
+          tc::mbar_arrive_expect_tx(&bar_full[s], a.w_bytes + 4u * a.x_chunk_bytes);
           tc::bulk_g2s(sw, wsrc + (size_t)i * (a.w_bytes / 4), a.w_bytes, &bar_full[s]);
-        }
-        __syncwarp();
-        if (ncopy > 0) {
-          // one copy per (sample, 4-channel plane): lanes issue them in parallel
-          for (int u = lane; u < c.nsamp * 4; u += 32) {
-            const int g = u >> 2, q = u & 3;
-            tc::bulk_g2s(sx + (size_t)q * a.x_chunk_bytes + ((size_t)g * a.R + r_lo) * 16,
-                         d.in + (size_t)(c.b0 + g) * d.in_bstride + ((size_t)(i * 4 + q) * d.Tin + p_lo) * 4, (uint32_t)ncopy * 16u,
-                         &bar_full[s]);
-          }
+          tc::tensor_g2s_4d(sw + a.w_bytes, &tmx, 0, tstart, c.b0, i * 4, &bar_full[s]);
         }
         __syncwarp();
         if (++s == a.nstage) { s = 0; ph ^= 1u; first_round = false; }
@@ -172,7 +166,7 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a)
       const uint32_t dcol = tb + buf * 256u;
       for (int i = 0; i < a.nslab; ++i) {
         const long long w0 = a.dbg ? clock64() : 0;
-        ok = __all_sync(0xffffffffu, tc::mbar_wait(&bar_ready[s], ph, a.status, 3));
+        ok = __all_sync(0xffffffffu, tc::mbar_wait(a.patch ? &bar_ready[s] : &bar_full[s], ph, a.status, 3));
         const long long w1 = a.dbg ? clock64() : 0;
         dbg0 += w1 - w0;
         if (!ok) break;
@@ -214,22 +208,27 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a)
     }
   } else if (warp >= 4 && warp < 8) {
     // ================================================================ patch warps (128 threads)
-    // rows of the staged tile that are not input data (reflect / zero halo at the ends of a sample) are
-    // written from global memory; data rows are rounded to TF32 in place unless the producer of the
-    // input already rounded them (AVC_F_IN_TF32)
+    // (a) reflect padding: the copy engine delivered zeros for the rows outside the sample; they are overwritten
+    //     with their mirror rows, taken from the staged rows of the same sample (from global memory only when a
+    //     time-tiled sample's mirror row lies outside the tile);
+    // (b) TF32 rounding, when the producer of the input did not round it (AVC_F_IN_TF32 unset: the residual
+    //     stream stays full fp32 like the reference's activations): every row is rounded to nearest in place, so
+    //     that the tensor core's truncation is exact.
+    // a.patch == 0 (zero padding or K = 1, pre-rounded input): these warps idle, the MMAs wait on the copies directly.
     const int ptid = tid - 128;
     const bool rnd = !(d.flags & AVC_F_IN_TF32);
+    const bool refl = d.pad_mode == AVC_PAD_REFLECT;
     int s = 0;
     uint32_t ph = 0;
     bool ok = true;
     long long dbg0 = 0, dbg1 = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles && ok; tile += gridDim.x) {
+    for (int tile = blockIdx.x; a.patch && tile < a.ntiles && ok; tile += gridDim.x) {
       const TileCoord c = t2_decode(a, tile);
       const int pbeg = c.t0 * S - d.pad_left;
       const int nr = (c.tw - 1) * S + K;  // rows one sample needs
-      const int p_lo = max(0, pbeg), p_hi = min(d.Tin, pbeg + nr);
-      const int ncopy = max(0, p_hi - p_lo), r_lo = p_lo - pbeg;
-      const int nh = nr - ncopy;
+      const int p_lo = max(0, pbeg), p_hi = min(d.Tin, pbeg + a.R);   // input positions present in the staged rows
+      const int ncopy = max(0, min(p_hi, pbeg + nr) - p_lo), r_lo = p_lo - pbeg;
+      const int nh = refl ? nr - ncopy : 0;
       for (int i = 0; i < a.nslab && ok; ++i) {
         const long long w0 = a.dbg ? clock64() : 0;
         ok = tc::mbar_wait(&bar_full[s], ph, a.status, 4);
@@ -237,27 +236,31 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a)
         dbg0 += w1 - w0;
         if (!ok) break;
         float4* sx = reinterpret_cast<float4*>(smem + (size_t)s * a.stage_bytes + a.w_bytes);
+        bool wrote = false;
         if (rnd) {
-          for (int r = ptid; r < c.nsamp * ncopy; r += 128) {
+          for (int e = ptid; e < c.nsamp * ncopy * 4; e += 128) {
+            const int q = e & 3, r = e >> 2;
             const int g = r / ncopy, t = r - g * ncopy;
-            float4* p = sx + g * a.R + r_lo + t;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) p[(size_t)q * a.srows] = t2_round4(p[(size_t)q * a.srows]);
+            float4* p = sx + (size_t)q * a.srows + g * a.R + r_lo + t;
+            *p = t2_round4(*p);
+            wrote = true;
           }
         }
-        for (int r = ptid; r < c.nsamp * nh; r += 128) {
+        // halo rows: one (sample, row, 4-channel plane) per thread.  A source row may be rounded in place by
+        // another thread at the same time: rounding is idempotent, either version gives the same result.
+        for (int e = ptid; e < c.nsamp * nh * 4; e += 128) {
+          const int q = e & 3, r = e >> 2;
           const int g = r / nh, h = r - g * nh;
           const int u = h < r_lo ? h : h + ncopy;  // row inside the sample's segment
-          const int p = src_pos(pbeg + u, d.Tin, d.pad_mode, 1);
-          const float* src = d.in + (size_t)(c.b0 + g) * d.in_bstride + ((size_t)(i * 4) * d.Tin + (p >= 0 ? p : 0)) * 4;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 v = p >= 0 ? ldg4(src + (size_t)q * d.Tin * 4) : zero4();
-            if (rnd) v = t2_round4(v);
-            sx[(size_t)q * a.srows + g * a.R + u] = v;
-          }
+          const int p = src_pos(pbeg + u, d.Tin, AVC_PAD_REFLECT, 1);
+          float4 v = zero4();
+          if (p >= p_lo && p < p_hi) v = sx[(size_t)q * a.srows + g * a.R + (p - pbeg)];
+          else if (p >= 0) v = ldg4(d.in + (size_t)(c.b0 + g) * d.in_bstride + ((size_t)(i * 4 + q) * d.Tin + p) * 4);
+          if (rnd) v = t2_round4(v);
+          sx[(size_t)q * a.srows + g * a.R + u] = v;
+          wrote = true;
         }
-        tc::fence_proxy_async_smem();
+        if (wrote) tc::fence_proxy_async_smem();   // only writers pay for the proxy fence
         tc::mbar_arrive(&bar_ready[s]);
         if (a.dbg) dbg1 += clock64() - w1;
         if (++s == a.nstage) { s = 0; ph ^= 1u; }
@@ -287,10 +290,11 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a)
     const bool rnd_out = (d.flags & AVC_F_ROUND_OUT) != 0;
     bool ok = true;
     int tl = 0;
-    long long dbg0 = 0, dbg1 = 0, dbg2 = 0, dbg3 = 0;
+    long long dbg0 = 0, dbg1 = 0, dbg2 = 0, dbg3 = 0, dbg4 = 0, dbg5 = 0;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tl) {
       const TileCoord c = t2_decode(a, tile);
       const uint32_t buf = (uint32_t)tl & 1u;
+      long long e3b = 0;
       const long long e0 = a.dbg ? clock64() : 0;
       ok = tc::mbar_wait(&bar_accf[buf], (uint32_t)(tl >> 1) & 1u, a.status, 5) && ok;
       tc::tc_fence_after();
@@ -307,23 +311,31 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a)
         for (int g = 0; g < c.nsamp; ++g) {
           float s1 = 0.f, s2 = 0.f;
           float* sdst = srow + (size_t)(g * Ts) * 4;
-          for (int j = half; j < nch; j += 2) {
-            float v[16];
-            tc::tmem_ld16(lane_addr + (uint32_t)(g * a.R + 16 * j), v);
+          for (int j = half; j < nch; j += 4) {   // this warp's chunks j, j+2, ...: two loads in flight per wait
+            float v[32];
+            const bool two = j + 2 < nch;
+            tc::tmem_ld16_nowait(lane_addr + (uint32_t)(g * a.R + 16 * j), v);
+            if (two) tc::tmem_ld16_nowait(lane_addr + (uint32_t)(g * a.R + 16 * (j + 2)), v + 16);
+            tc::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int col = 16 * j + i;
-              if (col < ncol && (col & smask) == 0) {
-                const float x = v[i] + bias;
-                s1 += x;
-                s2 = fmaf(x, x, s2);
-                sdst[(size_t)(col >> sshift) * 4] = x;
+            for (int k = 0; k < 2; ++k) {
+              if (k == 1 && !two) break;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int col = 16 * (j + 2 * k) + i;
+                if (col < ncol && (col & smask) == 0) {
+                  const float x = v[16 * k + i] + bias;
+                  s1 += x;
+                  s2 = fmaf(x, x, s2);
+                  sdst[(size_t)(col >> sshift) * 4] = x;
+                }
               }
             }
           }
           if (d.norm) stat[(half * a.G + g) * 128 + col_l] = make_float2(s1, s2);
         }
       }
+      if (a.variant) tc::fence_proxy_async_smem();   // the staged rows will be read by bulk (async-proxy) stores
       tc::tc_fence_before();
       tc::mbar_arrive(&bar_acce[buf]);  // the accumulator is free: the MMA warp may start tile tl+2 into it
       const long long e2 = a.dbg ? clock64() : 0;
@@ -404,14 +416,26 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a)
             }
           }
         } else {
+          const bool bulk_c = (a.variant & 1) != 0;
+          const bool bulk_y = (a.variant & 2) != 0 && !shuf && ots == 1;
           if (d.save_c) {  // raw conv (+bias) rows in conv layout, kept for the backward pass
             for (int row = ewarp; row < c.nsamp * nq; row += 8) {
               const int g = row / nq, cql = row - g * nq;
               const float4* sr = st4p + (size_t)cql * P + g * Ts;
               float* cb = d.save_c + (((size_t)(c.b0 + g) * (d.Cout >> 2) + (c.mtile * 32 + cql)) * d.Tout + c.t0) * 4;
-              for (int t = lane; t < c.tw; t += 32) st4(cb + (size_t)t * 4, sr[t]);
+              if (bulk_c) {   // one bulk (TMA) store per row: the copy engine moves it, no LSU traffic
+                if (lane == 0) tc::bulk_s2g(cb, sr, (uint32_t)c.tw * 16u);
+              } else {
+                for (int t = lane; t < c.tw; t += 32) st4(cb + (size_t)t * 4, sr[t]);
+              }
             }
+            if (bulk_c && lane == 0) {
+              tc::bulk_commit();
+              if (bulk_y) tc::bulk_wait_read_all();   // the rows are about to be overwritten in place
+            }
+            __syncwarp();
           }
+          if (a.dbg) e3b = clock64();
           const int nqo = shuf ? nq >> 1 : nq;       // output chunks of this tile
           const int two = shuf ? c.tw * 2 : c.tw;    // output time steps of this tile
           const int to0 = shuf ? c.t0 * 2 : c.t0;    // first output time step of this tile
@@ -472,28 +496,40 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a)
                 o.x = m.x > 0.f ? o.x : 0.f; o.y = m.y > 0.f ? o.y : 0.f; o.z = m.z > 0.f ? o.z : 0.f; o.w = m.w > 0.f ? o.w : 0.f;
               }
               if (rnd_out) o = t2_round4(o);
-              st4(ob + (size_t)(t * ots + oto) * 4, o);
+              if (bulk_y) const_cast<float4*>(srA)[tl_] = o;   // in place: this warp owns the row
+              else st4(ob + (size_t)(t * ots + oto) * 4, o);
             }
+            if (bulk_y) {
+              tc::fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) tc::bulk_s2g(ob + (size_t)(to0 + oto) * 4, srA, (uint32_t)two * 16u);
+            }
+          }
+          if ((bulk_c || bulk_y) && lane == 0) {
+            tc::bulk_commit();
+            tc::bulk_wait_read_all();   // the staged tile is rewritten by the next tile's TMEM pass
           }
         }
       }
+      const long long e3c = a.dbg ? clock64() : 0;
       t2_bar_sync(2, 256);  // the staged tile and the parameter arrays are reused by the next tile
       if (a.dbg) {
         const long long e4 = clock64();
-        dbg0 += e1 - e0; dbg1 += e2 - e1; dbg2 += e3 - e2; dbg3 += e4 - e3;
+        if (e3b == 0) e3b = e3;
+        dbg0 += e1 - e0; dbg1 += e2 - e1; dbg2 += e3 - e2; dbg3 += e3b - e3; dbg4 += e3c - e3b; dbg5 += e4 - e3c;
       }
     }
     if (a.dbg && etid == 0) {
       long long* o = a.dbg + (size_t)blockIdx.x * 16;
-      o[8] = dbg0; o[9] = dbg1; o[10] = dbg2; o[11] = dbg3; o[12] = tl;
+      o[8] = dbg0; o[9] = dbg1; o[10] = dbg2; o[11] = dbg3; o[12] = tl; o[13] = dbg4; o[14] = dbg5;
     }
   }
+  tc::tc_fence_before();
+  __syncthreads();
   if (a.dbg && tid == 0) {
     long long* o = a.dbg + (size_t)blockIdx.x * 16;
     o[0] = tm0; o[1] = clock64();
   }
-  tc::tc_fence_before();
-  __syncthreads();
   if (warp == 2) tc::tmem_dealloc(tbase, 512u);
 }
 
@@ -519,6 +555,8 @@ int t2_plan(const avc_conv_desc* d, Tc2Args& a) {
   a.w_bytes = (uint32_t)K * T2_WTAP_BYTES;
   a.mtiles = cdiv(d->Cout, 128);
   const int ncol_full = (d->Tout - 1) * S + 1;
+  if (d->pad_mode == AVC_PAD_REFLECT && d->Tin <= d->pad_left) return AVC_ERR_UNSUPPORTED;   // no mirror row to copy
+  if (d->in_bstride % 4 != 0 || ((uintptr_t)d->in & 15u)) return AVC_ERR_UNSUPPORTED;        // tensor-map strides are multiples of 16 bytes
   if (ncol_full <= 144) {
     a.TT = d->Tout;
     a.ntt = 1;
@@ -548,9 +586,11 @@ int t2_plan(const avc_conv_desc* d, Tc2Args& a) {
   if (bestG == 0) return AVC_ERR_UNSUPPORTED;
   a.G = bestG;
   a.N = ((a.G - 1) * a.R + ncol + 15) / 16 * 16;
-  a.srows = (a.N + K - 1 + 7) / 8 * 8;
+  a.srows = a.G * a.R;   // one plane of the tensor-copy box: [G samples][R rows] of 16 bytes
   a.x_chunk_bytes = (uint32_t)a.srows * 16u;
-  a.stage_bytes = (a.w_bytes + 4u * a.x_chunk_bytes + 1023u) / 1024u * 1024u;
+  // an N-column MMA reads up to N + K - 1 rows of the last plane, at most 15 + K rows past its end (garbage columns):
+  // keep that inside the stage
+  a.stage_bytes = (a.w_bytes + 4u * a.x_chunk_bytes + 32u * 16u + 1023u) / 1024u * 1024u;
   a.ngroups = cdiv(d->B, a.G);
   a.ntiles = a.ngroups * a.ntt * a.mtiles;
   // staged tile: 32 chunks, pitch == 1 mod 8 sixteen-byte units
@@ -569,7 +609,25 @@ int t2_plan(const avc_conv_desc* d, Tc2Args& a) {
   return AVC_OK;
 }
 
+typedef CUresult (*PFN_t2_encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// the driver entry point is fetched through the runtime: the library does not link against libcuda
+static PFN_t2_encode t2_encode_fn() {
+  void* f = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+  return (PFN_t2_encode)f;
+}
+
 static long long* g_tc2_dbg = nullptr;
+static int g_tc2_variant = -1;
+static int t2_variant() {
+  if (g_tc2_variant < 0) {
+    const char* e = getenv("AVC_T2_VARIANT");
+    g_tc2_variant = e ? atoi(e) : 0;
+  }
+  return g_tc2_variant;
+}
 
 int conv_block_tc2_launch(const avc_conv_desc* d, int* status, void* stream) {
   Tc2Args a;
@@ -577,6 +635,27 @@ int conv_block_tc2_launch(const avc_conv_desc* d, int* status, void* stream) {
   if (rc != AVC_OK) return rc;
   a.status = status;
   a.dbg = g_tc2_dbg;
+  a.patch = (!(d->flags & AVC_F_IN_TF32) || (d->pad_mode == AVC_PAD_REFLECT && d->K > 1)) ? 1 : 0;
+  a.variant = t2_variant();
+  CUtensorMap tmx;
+  {
+    static PFN_t2_encode enc = t2_encode_fn();
+    if (!enc) {
+      set_error("avc_conv_block_tc: cuTensorMapEncodeTiled is not available from this driver");
+      return AVC_ERR_CUDA;
+    }
+    const cuuint64_t gdim[4] = {4, (cuuint64_t)d->Tin, (cuuint64_t)d->B, (cuuint64_t)(d->Cin / 4)};
+    const cuuint64_t gstr[3] = {16, (cuuint64_t)d->in_bstride * 4u, (cuuint64_t)d->Tin * 16u};
+    const cuuint32_t box[4] = {4, (cuuint32_t)a.R, (cuuint32_t)a.G, 4};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)d->in, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("avc_conv_block_tc: cuTensorMapEncodeTiled failed (%d) for Tin=%d B=%d Cin=%d bstride=%lld box R=%d G=%d", (int)r, d->Tin, d->B,
+                d->Cin, (long long)d->in_bstride, a.R, a.G);
+      return AVC_ERR_CUDA;
+    }
+  }
   const int smem = (int)(a.off_stat + 2u * (uint32_t)a.G * 128u * 8u);
   static bool attr_done = false;
   if (!attr_done) {
@@ -588,7 +667,7 @@ int conv_block_tc2_launch(const avc_conv_desc* d, int* status, void* stream) {
     attr_done = true;
   }
   const int grid = a.ntiles < t2_num_sms() ? a.ntiles : t2_num_sms();
-  AVC_LAUNCH(conv_block_tc2_kernel, grid, 512, smem, (cudaStream_t)stream, a);
+  AVC_LAUNCH(conv_block_tc2_kernel, grid, 512, smem, (cudaStream_t)stream, a, tmx);
   AVC_CHECK_LAUNCH("conv_block_tc2");
   return AVC_OK;
 }
@@ -596,3 +675,4 @@ int conv_block_tc2_launch(const avc_conv_desc* d, int* status, void* stream) {
 }  // namespace avc
 
 extern "C" void avc_tc2_set_debug(void* dev_buffer) { avc::g_tc2_dbg = (long long*)dev_buffer; }
+extern "C" void avc_tc2_set_variant(int v) { avc::g_tc2_variant = v; }

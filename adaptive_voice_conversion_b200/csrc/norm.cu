@@ -247,12 +247,22 @@ __global__ void __launch_bounds__(256) norm_bwd_kernel(const avc_conv_desc d) {
 
 // norm_bwd for the common training shape (no pixel shuffle, Tout <= 128): the row of `c` and of
 // `dy` is read ONCE into registers (4 float4 each per lane) and reused by both passes.
+// Warps are numbered chunk-major (the 8 warps of a block work on the SAME 4-channel chunk of 8 consecutive
+// samples), so the bias gradient is reduced inside the block first: one atomic per channel per block instead of
+// one per warp (32 768 atomics on 128 addresses at B=256 were a measurable part of this kernel).
 __global__ void __launch_bounds__(256) norm_bwd_cached_kernel(const avc_conv_desc d) {
-  const int Cn = d.Cout, Tn = d.Tout, Cnq = Cn >> 2;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= d.B * Cnq) return;
-  const int b = warp / Cnq, qn = warp - b * Cnq;
+  __shared__ float db_sh[8][4];
+  const int Cn = d.Cout, Tn = d.Tout;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int bgroups = (d.B + 7) >> 3;                  // blocks per chunk
+  const int qn = blockIdx.x / bgroups, b = (blockIdx.x - qn * bgroups) * 8 + wib;
+  const bool live = b < d.B;                           // dead warps still join the block reduction below
+  if (!live && !d.dbias) return;
+  if (!live) {
+    if (lane < 4) db_sh[wib][lane] = 0.f;
+    __syncthreads();
+    return;
+  }
   const float* cb = d.save_c + (int64_t)b * d.Cout * d.Tout + (int64_t)qn * d.Tout * 4;
   const float* dyb = d.dy + (int64_t)b * d.dy_bstride + (int64_t)qn * Tn * 4;
   float mean[4] = {0, 0, 0, 0}, rstd[4] = {1, 1, 1, 1}, beta[4] = {0, 0, 0, 0}, gamma[4] = {1, 1, 1, 1};
@@ -325,7 +335,14 @@ __global__ void __launch_bounds__(256) norm_bwd_cached_kernel(const avc_conv_des
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const float s = warp_sum(db[c]);
-      if (lane == 0) atomicAdd(d.dbias + qn * 4 + c, s);
+      if (lane == 0) db_sh[wib][c] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += db_sh[w][threadIdx.x];
+      atomicAdd(d.dbias + qn * 4 + threadIdx.x, s);
     }
   }
 }
@@ -423,7 +440,7 @@ extern "C" int avc_norm_bwd(const avc_conv_desc* d, void* stream) {
   const int64_t warps = (int64_t)d->B * (Cn / 4);
   const int blocks = (int)cdiv64(warps * 32, 256);
   if (d->shuffle) AVC_LAUNCH(norm_bwd_kernel<true>, blocks, 256, 0, (cudaStream_t)stream, *d);
-  else if (d->Tout <= 128) AVC_LAUNCH(norm_bwd_cached_kernel, blocks, 256, 0, (cudaStream_t)stream, *d);
+  else if (d->Tout <= 128) AVC_LAUNCH(norm_bwd_cached_kernel, (Cn / 4) * ((d->B + 7) / 8), 256, 0, (cudaStream_t)stream, *d);
   else AVC_LAUNCH(norm_bwd_kernel<false>, blocks, 256, 0, (cudaStream_t)stream, *d);
   AVC_CHECK_LAUNCH("norm_bwd");
   return AVC_OK;

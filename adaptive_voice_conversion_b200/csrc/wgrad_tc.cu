@@ -24,6 +24,7 @@ constexpr int WT_NT = 64;  // ci columns per CTA
 struct WgTcArgs {
   avc_wgrad_desc d;
   float* scratch;
+  long long* dbg;   // optional per-CTA phase cycle counters (avc_wgrad_tc_set_debug)
   int nslices, tiles_per_slice, G, RA, RX, ntpad, ncols_tmem, coutp, TX, H;  // H: rows of one parity block (stride 2)
   uint32_t buf_bytes, x_off;
   int* status;
@@ -82,11 +83,15 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
   const int nq_x = a.ntpad >> 2;  // 16-byte units per row of the x operand
   bool ok = true;
   const uint32_t smem_base = tc::smem_u32(smem);
+  long long t_begin = 0, c_stage = 0, c_free = 0, c_issue = 0;
+  if (a.dbg) t_begin = clock64();
 
   for (int tile = tile0; tile < tile1; ++tile) {
     const int it = tile - tile0;
     const int buf = it & 1;
+    const long long q0 = a.dbg ? clock64() : 0;
     if (it >= 2) ok = tc::mbar_wait(&bar_free[buf], (uint32_t)((it >> 1) - 1) & 1u, a.status, 6) && ok;
+    const long long q1 = a.dbg ? clock64() : 0;
     uint8_t* sA = smem + (size_t)buf * a.buf_bytes;
     uint8_t* sX = sA + a.x_off;
     const int b0 = tile * a.G;
@@ -123,6 +128,9 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     tc::fence_proxy_async_smem();
     ok = __syncthreads_and(ok) != 0;  // also makes `ok` block-uniform for the issue loop below
+    const long long q2 = a.dbg ? clock64() : 0;
+    c_free += q1 - q0;
+    c_stage += q2 - q1;
     if (warp == 0) {  // warp-converged issue loop, one elected lane per instruction (uniform descriptors)
       if (__all_sync(0xffffffffu, ok)) {
         if constexpr (UI) {
@@ -198,15 +206,18 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
         __syncwarp();
         if (tc::elect_one()) tc::mma_commit(&bar_free[buf]);
       }
+      if (a.dbg) c_issue += clock64() - q2;
     }
   }
   if (warp == 0) {
     __syncwarp();
     if (tc::elect_one()) tc::mma_commit(&bar_done);
   }
+  const long long q3 = a.dbg ? clock64() : 0;
   ok = tc::mbar_wait(&bar_done, 0, a.status, 7) && ok;
   ok = __syncthreads_and(ok) != 0;
   tc::tc_fence_after();
+  const long long q4 = a.dbg ? clock64() : 0;
   if (ok && tile1 > tile0) {
     // partial dW of this slice: scratch[sl][tap][ci/4][co][4]
     const int co = co0 + tid;
@@ -232,6 +243,11 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (a.dbg && tid == 0) {
+    long long* o = a.dbg + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8;
+    const long long q5 = clock64();
+    o[0] = t_begin; o[1] = q5; o[2] = c_stage; o[3] = c_free; o[4] = c_issue; o[5] = q4 - q3; o[6] = q5 - q4; o[7] = tile1 - tile0;
+  }
   if (warp == 0) tc::tmem_dealloc(tbase, (uint32_t)a.ncols_tmem);
 }
 
@@ -343,6 +359,7 @@ extern "C" int64_t avc_wgrad_tc_scratch_floats(const avc_wgrad_desc* d) {
   return (int64_t)a.nslices * d->K * d->Cin * a.coutp;
 }
 
+static long long* g_wg_dbg = nullptr;
 static int wgrad_tc_launch(const avc_wgrad_desc* d, float* scratch, int* status, void* stream, bool accumulate, const char* who) {
   AVC_REQUIRE(d && d->x && d->dc && scratch && status && (accumulate || d->dw), AVC_ERR_INVALID, "%s: null argument", who);
   AVC_REQUIRE(d->B > 0 && d->Cin > 0 && d->Cout > 0 && d->Tin > 0 && d->Tout > 0, AVC_ERR_INVALID, "%s: bad shape", who);
@@ -351,6 +368,7 @@ static int wgrad_tc_launch(const avc_wgrad_desc* d, float* scratch, int* status,
   wgrad_tc_plan(d, a);
   a.scratch = scratch;
   a.status = status;
+  a.dbg = g_wg_dbg;
   const int smem = 2 * (int)a.buf_bytes;
   AVC_REQUIRE(smem <= 224 * 1024, AVC_ERR_UNSUPPORTED, "%s: tile does not fit shared memory", who);
   static bool attr_done = false;
@@ -400,3 +418,5 @@ extern "C" int avc_wgrad_acc_flush(const avc_wgrad_acc_item* items_dev, int n_it
   AVC_CHECK_LAUNCH("wgrad_acc_flush");
   return AVC_OK;
 }
+
+extern "C" void avc_wgrad_tc_set_debug(void* dev_buffer) { g_wg_dbg = (long long*)dev_buffer; }

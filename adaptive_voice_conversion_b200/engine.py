@@ -106,6 +106,10 @@ class Engine:
         self.fold_fused = os.environ.get("AVC_FOLD_FUSED", "1" if L.DEFAULT_FOLD_FUSED else "0") == "1"
         self._wg_acc = None
         self.tc_conv_v2 = bool(self.lib.avc_get_option(b"tc_conv_v2"))
+        # diagnostic (tools/diag_tf32.py, tests/test_gpu_tf32_accuracy.py): forward conv blocks on the exact-fp32 FFMA
+        # kernels while the backward stays on the tensor cores -- separates "TF32 forward flips ReLU masks" from
+        # "TF32 backward kernels are inaccurate" in the gradient-parity numbers
+        self.fwd_fp32 = os.environ.get("AVC_FWD_FP32", "0") == "1"
 
     # ------------------------------------------------------------------ utilities
     @property
@@ -164,7 +168,7 @@ class Engine:
     def pack_a4(self, planar: torch.Tensor, dst: A4):
         B, Cc, T = planar.shape
         assert planar.is_contiguous() and planar.dtype == torch.float32
-        rnd = 1 if self.precision == "tf32" else 0
+        rnd = 1 if (self.precision == "tf32" and not self.fwd_fp32) else 0
         self._ck(self.lib.avc_pack_a4(planar.data_ptr(), dst.ptr, dst.bstride, B, Cc, T, rnd, self.stream), "pack_a4")
         if rnd and dst.bstride == dst.C * dst.T:
             dst.tf32 = True
@@ -292,24 +296,27 @@ class Engine:
             out = A4.empty(B, Cn, Tn, self.dev)
         assert (out.C, out.T) == (Cn, Tn)
         need_c = train and (norm or relu)
-        # tcgen05 path: one tile per sample up to 256 columns; longer samples are time-tiled by the persistent
-        # kernel when the block has no whole-sample statistics (no InstanceNorm / pixel shuffle)
-        use_tc = (self.precision == "tf32" and Cin % 16 == 0 and not (stride == 2 and shuffle) and "fwd_tc" in self.packed[name]
-                  and (Tout * stride <= 256 or (self.tc_conv_v2 and not norm and not shuffle)))
-        fused = use_tc or (not norm) or (Tout <= 128) or (Tout <= 256 and K in (1, 5))
+        # tcgen05 path: one tile per sample up to 256 columns (fused block).  Longer samples (inference) are
+        # time-tiled by the persistent kernel: fused when the block has no whole-sample statistics, otherwise
+        # as a plain conv whose raw output avc_norm_apply_fwd finishes (shuffle / InstanceNorm / AdaIN / residual)
+        tc_ok = (self.precision == "tf32" and not self.fwd_fp32 and Cin % 16 == 0 and not (stride == 2 and shuffle)
+                 and "fwd_tc" in self.packed[name])
+        use_tc = tc_ok and (Tout * stride <= 256 or (self.tc_conv_v2 and not norm and not shuffle))
+        tc_split = tc_ok and not use_tc and self.tc_conv_v2 and norm
+        fused = use_tc or (not tc_split and ((not norm) or (Tout <= 128) or (Tout <= 256 and K in (1, 5))))
         c = A4.empty(B, Cout, Tout, self.dev) if (need_c or not fused) else None
         stats = self.empty(B, Cn, 2) if norm else None
         d = L.ConvDesc()
         d.B, d.Cin, d.Cout, d.K, d.stride = B, Cin, Cout, K, stride
         d.pad_left, d.pad_mode, d.in_ups, d.Tin, d.Tout = pl, L.PAD_REFLECT, 1, xin.T, Tout
         d.in_, d.in_bstride = xin.ptr, xin.bstride
-        if not use_tc:
+        if not (use_tc or tc_split):
             self._ensure_simt_pack(P, name, "fwd")
             d.w_packed = self.packed[name]["fwd"].data_ptr()
         d.w_ld = Cout
         d.bias = P[name + ".bias"].data_ptr()
         d.eps = IN_EPS
-        if self.precision == "tf32":
+        if self.precision == "tf32" and not self.fwd_fp32:
             d.flags = (L.F_ROUND_OUT if round_out else 0) | (L.F_IN_TF32 if xin.tf32 else 0)
             if round_out and out.bstride == out.C * out.T:
                 out.tf32 = True
@@ -323,7 +330,14 @@ class Engine:
                 self._ck(self.lib.avc_conv_block_fwd(C.byref(d), self.stream), f"conv_block_fwd[{name}]")
         else:
             d.out, d.out_bstride = c.ptr, c.bstride
-            self._ck(self.lib.avc_conv_block_fwd(C.byref(d), self.stream), f"conv_block_fwd[{name}]")
+            if tc_split:
+                flags = int(d.flags)
+                d.flags = flags & ~L.F_ROUND_OUT     # the raw conv output feeds the statistics: keep it fp32
+                d.w_tc = self.packed[name]["fwd_tc"].data_ptr()
+                self._ck(self.lib.avc_conv_block_tc(C.byref(d), self.tc_status.data_ptr(), self.stream), f"conv_tc_plain[{name}]")
+                d.flags = flags
+            else:
+                self._ck(self.lib.avc_conv_block_fwd(C.byref(d), self.stream), f"conv_block_fwd[{name}]")
             self._fill_epilogue(d, out, shuffle, norm, relu, cond, res, res_mode, stats)
             d.save_c = c.ptr
             self._ck(self.lib.avc_norm_apply_fwd(C.byref(d), self.stream), f"norm_apply_fwd[{name}]")
@@ -421,7 +435,10 @@ class Engine:
                 d.cond, d.cond_bstride = rec["cond"].data_ptr(), rec["cond"].stride(0)
                 d.dcond, d.dcond_bstride = dcond.data_ptr(), dcond.stride(0)
             d.dy, d.dy_bstride = dy.ptr, dy.bstride
-            d.dc, d.dbias = dc.ptr, gb.data_ptr()
+            # the bias of a conv that feeds an InstanceNorm has an identically zero gradient (the norm removes the
+            # per-channel mean); autograd returns ~1e-9 rounding noise there, we leave the zeroed buffer untouched
+            # (not with pixel shuffle: there two conv rows with different biases share one normalised channel)
+            d.dc, d.dbias = dc.ptr, (None if (rec["norm"] and not rec["shuffle"]) else gb.data_ptr())
             if self.precision == "tf32":
                 d.flags = L.F_ROUND_OUT
                 dc.tf32 = True
@@ -549,7 +566,7 @@ class Engine:
                              round_out=True)   # the concat is read by in_conv (and its weight gradient) only
             recs.append(r)
         # every writer of `cat` (pack_a4 and the bank convs' epilogues) rounds to TF32 in tf32 mode
-        cat.tf32 = self.precision == "tf32"
+        cat.tf32 = self.precision == "tf32" and not self.fwd_fp32
         out, rec_in = self.conv(P, f"{enc}.in_conv_layer", cat, norm=norm, relu=True, train=train)
         if train:
             ctx["cat"], ctx["x4"], ctx["in"] = cat, x4, rec_in

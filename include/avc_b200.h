@@ -124,8 +124,14 @@ int64_t avc_tc_packed_floats(int co_total, int ci_total, int K);
 void avc_tc_set_debug(void* dev_buffer);
 /* Same for the persistent kernel: 16 int64 per CTA: [0] start [1] end clock; wait / work cycle sums of the roles:
  * [2] producer wait-empty, [3] patch wait-full [4] patch work, [5] MMA wait-ready [6] wait-accumulator [7] issue,
- * [8] epilogue wait-accumulator [9] TMEM pass [10] parameters [11] store pass, [12] tiles done. */
+ * [8] epilogue wait-accumulator [9] TMEM pass [10] parameters [11] c rows [13] out rows [14] end barrier, [12] tiles done. */
 void avc_tc2_set_debug(void* dev_buffer);
+/* Weight-gradient kernel: 8 int64 per CTA: [0] start [1] end clock, cycle sums [2] staging [3] wait for a free buffer
+ * [4] MMA issue [5] wait for the last MMAs [6] epilogue, [7] tiles. */
+void avc_wgrad_tc_set_debug(void* dev_buffer);
+/* Store path of the persistent kernel's second pass (default from AVC_T2_VARIANT): bit 0 = `c` rows through bulk
+ * (TMA) stores, bit 1 = `out` rows written back in place and bulk-stored. */
+void avc_tc2_set_variant(int v);
 /* Runtime options (process-wide; each also has an environment default read on first use):
  *   "tc_uniform_issue"  (AVC_TC_ISSUE=uniform|legacy)   tcgen05 issue loops on the uniform datapath
  *   "wgrad_reduce_v2"   (AVC_WGRAD_REDUCE=v2|v1)        unrolled partial-sum reduction of conv_wgrad_tc

@@ -39,16 +39,22 @@ for (Cin, Cout, K, T, kw, tag) in [(128, 128, 5, 128, dict(norm=True, relu=True)
     except Exception as e:
         v1_us = float("nan")
     L.set_option("tc_conv_v2", True)
-    dbg = torch.zeros(16 * 256, dtype=torch.int64, device=dev)
-    eng.lib.avc_tc2_set_debug(dbg.data_ptr())
-    eng.conv(P, "r", x, train=train, **kw)
-    torch.cuda.synchronize()
-    eng.lib.avc_tc2_set_debug(None)
-    t = dbg.view(-1, 16).cpu()
-    t = t[t[:, 0] != 0]
-    f = lambda i: float(t[:, i].float().mean())
-    span = float(t[:, 1].max() - t[:, 0].min())
-    print(f"{tag:18s} {e0.elapsed_time(e1) * 100:7.1f} us/launch (hot L2; round-1 kernel {v1_us:7.1f} us)  CTAs {len(t)}  tiles/CTA {f(12):.2f}  CTA life {float((t[:,1]-t[:,0]).float().mean()):8.0f} cyc  span {span:8.0f}")
-    print(f"{'':18s} producer wait-empty {f(2):7.0f} | patch wait-full {f(3):7.0f} work {f(4):7.0f} | mma wait-ready {f(5):7.0f} wait-acc {f(6):7.0f} issue {f(7):7.0f}"
-          f" | epi wait-acc {f(8):7.0f} tmem-pass {f(9):7.0f} params {f(10):7.0f} store-pass {f(11):7.0f}", flush=True)
+    for variant in (0, 1, 3):
+        eng.lib.avc_tc2_set_variant(variant)
+        for _ in range(2):
+            eng.conv(P, "r", x, train=train, **kw)
+        dbg = torch.zeros(16 * 256, dtype=torch.int64, device=dev)
+        eng.lib.avc_tc2_set_debug(dbg.data_ptr())
+        eng.conv(P, "r", x, train=train, **kw)
+        torch.cuda.synchronize()
+        eng.lib.avc_tc2_set_debug(None)
+        t = dbg.view(-1, 16).cpu()
+        t = t[t[:, 0] != 0]
+        f = lambda i: float(t[:, i].float().mean())
+        life = (t[:, 1] - t[:, 0]).float()
+        if variant == 0:
+            print(f"{tag:18s} round-1 kernel {v1_us:6.1f} us/launch incl. python (hot L2)  CTAs {len(t)}  tiles/CTA {f(12):.2f}")
+        print(f"  variant {variant}: CTA life mean {life.mean():7.0f} max {life.max():7.0f} cyc = {life.max() / 1965:5.1f} us | producer wait-empty {f(2):6.0f} | patch wait-full {f(3):6.0f} work {f(4):6.0f}"
+              f" | mma wait-ready {f(5):6.0f} wait-acc {f(6):5.0f} issue {f(7):6.0f} | epi wait-acc {f(8):6.0f} tmem {f(9):5.0f} params {f(10):5.0f} c-rows {f(11):5.0f} out-rows {f(13):5.0f} end-bar {f(14):5.0f}", flush=True)
+    eng.lib.avc_tc2_set_variant(0)
 eng.check_tc_status()
