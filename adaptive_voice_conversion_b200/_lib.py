@@ -19,12 +19,17 @@ DEFAULT_WGRAD_ACC = True
 # engine.py: reflect-padding / residual adjoint inside the data-gradient conv's epilogue (AVC_F_FOLD, 30
 # avc_fold_add_fwd launches fewer per step).  ON since the round-2 validation (tests green, +0.5 %)
 DEFAULT_FOLD_FUSED = True
+# engine.py: the data-gradient conv of a block also runs the UPSTREAM block's InstanceNorm / AdaIN / ReLU backward in
+# its epilogue (AVC_F_NORMBWD, persistent kernel): 27 avc_norm_bwd launches and their dy/dc round trips fewer per step.
+# Validated on the B200 (tests/test_gpu_normbwd_fused.py, all model tests green) but SLOWER (47 853 vs 49 697 seg/s):
+# the conv kernel is bound by its 8 epilogue warps, the stand-alone avc_norm_bwd runs at full occupancy -> opt-in
+DEFAULT_NORM_BWD_FUSED = False
 LIB_PATH = os.environ.get("AVC_LIB", os.path.join(_PKG, "libavc_b200.so"))
 
 PAD_REFLECT, PAD_ZERO = 0, 1
 RES_NONE, RES_SAME, RES_POOL, RES_UP = 0, 1, 2, 3
 PACK_FWD, PACK_DGRAD = 0, 1
-F_ROUND_OUT, F_IN_TF32, F_FOLD = 1, 2, 4
+F_ROUND_OUT, F_IN_TF32, F_FOLD, F_NORMBWD = 1, 2, 4, 8
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
 
 _fp = C.c_void_p  # device pointers travel as integers
@@ -137,6 +142,7 @@ PROTOTYPES = {
     "avc_pack_a4": (_i, [_p, _p, _i64, _i, _i, _i, _i, _p]),
     "avc_unpack_a4": (_i, [_p, _i64, _p, _i, _i, _i, _p]),
     "avc_bias_grad": (_i, [_p, _i64, _p, _i, _i, _i, _p]),
+    "avc_bias_grad_groups": (_i, [_p, _i64, _p, _i, _i, _i, _i, _p]),
     "avc_time_mean_fwd": (_i, [_p, _i64, _p, _i, _i, _i, _p]),
     "avc_time_mean_bwd": (_i, [_p, _p, _i64, _i, _i, _i, _p]),
     "avc_linear_fwd": (_i, [C.POINTER(LinearDesc), _p]),
@@ -154,6 +160,7 @@ PROTOTYPES = {
     "avc_fill_zero": (_i, [_p, _i64, _p]),
     "avc_tc_probe_gemm": (_i, [_p, _i, _p, _i, C.POINTER(C.c_uint32), _i, _i, _i, _i, _i, _p, _p, _p]),
     "avc_tc_probe_set_ld_shift": (None, [_i]),
+    "avc_probe_store": (_i, [_p, C.c_longlong, _i, _i, _p, _p]),
     "avc_last_error": (C.c_char_p, []),
     "avc_build_info": (C.c_char_p, []),
     "avc_launch_count": (_i64, []),

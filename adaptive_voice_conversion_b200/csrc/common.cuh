@@ -18,6 +18,7 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int opt_tc_uniform_issue();  // runtime options, see avc_set_option
 int opt_wgrad_reduce_v2();
+int opt_wgrad_split();
 
 #define AVC_REQUIRE(cond, code, ...) \
   do {                               \

@@ -600,7 +600,10 @@ extern "C" void avc_tc_set_debug(void* dev_buffer) { g_tc_dbg = (long long*)dev_
 extern "C" int avc_conv_block_tc(const avc_conv_desc* d, int* status, void* stream) {
   int rc = validate_conv_desc(d, "avc_conv_block_tc");
   if (rc != AVC_OK) return rc;
-  AVC_REQUIRE(d->in && d->w_tc && d->out && status, AVC_ERR_INVALID, "avc_conv_block_tc: null in/w_tc/out/status");
+  const bool normbwd = (d->flags & AVC_F_NORMBWD) != 0;
+  AVC_REQUIRE(d->in && d->w_tc && (d->out || normbwd) && status, AVC_ERR_INVALID, "avc_conv_block_tc: null in/w_tc/out/status");
+  AVC_REQUIRE(!normbwd || ((d->flags & AVC_F_FOLD) && d->save_c && d->dc && (!d->norm || d->stats) && (!d->cond || d->dcond) && !d->shuffle),
+              AVC_ERR_INVALID, "avc_conv_block_tc: AVC_F_NORMBWD needs AVC_F_FOLD and the upstream block's save_c / stats / dc (dcond with cond)");
   AVC_REQUIRE((d->stride == 1 || d->stride == 2) && d->in_ups == 1, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: stride must be 1 or 2, in_ups 1");
   AVC_REQUIRE(d->stride == 1 || !d->shuffle, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: stride 2 with pixel shuffle");
   AVC_REQUIRE(d->out_tstride <= 1 || (!d->shuffle && !d->res && !d->mask && !d->norm), AVC_ERR_UNSUPPORTED,
@@ -608,7 +611,7 @@ extern "C" int avc_conv_block_tc(const avc_conv_desc* d, int* status, void* stre
   AVC_REQUIRE(d->K >= 1 && d->K <= 8, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: K=%d not in 1..8", d->K);
   if (d->flags & AVC_F_FOLD) {
     const int fpl = (d->flags >> 8) & 0xff, fpr = (d->flags >> 16) & 0xff;
-    AVC_REQUIRE(d->stride == 1 && !d->norm && !d->relu && !d->shuffle && !d->cond && !d->mask && !d->save_c && !d->bias && d->out_tstride <= 1,
+    AVC_REQUIRE(d->stride == 1 && !d->shuffle && !d->mask && !d->bias && d->out_tstride <= 1 && (normbwd || (!d->norm && !d->relu && !d->cond && !d->save_c)),
                 AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: AVC_F_FOLD is for plain stride-1 (data-gradient) convs");
     AVC_REQUIRE(fpl <= 4 && fpr <= 4 && d->Tout - fpl - fpr >= 2 * fpl + 1 && d->Tout - fpl - fpr >= fpr + 2, AVC_ERR_UNSUPPORTED,
                 "avc_conv_block_tc: AVC_F_FOLD pads (%d,%d) do not fit %d columns", fpl, fpr, d->Tout);
@@ -619,6 +622,7 @@ extern "C" int avc_conv_block_tc(const avc_conv_desc* d, int* status, void* stre
     const int rc2 = conv_block_tc2_launch(d, status, stream);
     if (rc2 != AVC_ERR_UNSUPPORTED) return rc2;
   }
+  AVC_REQUIRE(!normbwd, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: AVC_F_NORMBWD needs the persistent kernel and a one-tile shape (Tout <= 144, Cout <= 128)");
   const int ncols_full = d->stride == 2 ? 2 * d->Tout - 1 : d->Tout;  // stride 2: full-resolution columns 0 .. 2(Tout-1)
   AVC_REQUIRE(ncols_full <= 256, AVC_ERR_UNSUPPORTED, "avc_conv_block_tc: more than 256 columns per sample");
   AVC_REQUIRE(!d->res || d->res_mode != AVC_RES_NONE, AVC_ERR_INVALID, "avc_conv_block_tc: res without res_mode");

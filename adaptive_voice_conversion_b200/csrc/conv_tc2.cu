@@ -23,11 +23,11 @@
 //     data-gradient variant becomes three shared-memory reads.
 //   * Halo rows come straight from global memory (no dependence on the bulk copy), so long samples
 //     can be TIME-TILED (T > 144 columns: inference) for blocks without InstanceNorm.
-#include <cuda.h>
 #include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tmap.cuh"
 
 namespace avc {
 
@@ -68,6 +68,30 @@ __device__ __forceinline__ float4 t2_round4(float4 v) {
   return make_float4(t2_round_tf32(v.x), t2_round_tf32(v.y), t2_round_tf32(v.z), t2_round_tf32(v.w));
 }
 __device__ __forceinline__ void t2_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// Row hand-out of the store pass: row = (sample, 4-channel chunk) of the staged tile, lanes run along time.  Rows of
+// at most 16 time steps share a warp in pairs.  (g, cql) advance incrementally: a runtime division per row was a
+// 300-cycle dependent chain in front of every store.
+struct RowIter {
+  int row, g, cql, step, nq, tl0, tstep;
+};
+__device__ __forceinline__ RowIter t2_rows(int ewarp, int lane, int extent, int nq) {
+  RowIter r;
+  const int lpr = extent <= 16 ? 16 : 32, rpp = 32 / lpr;
+  r.row = ewarp * rpp + lane / lpr;
+  r.step = 8 * rpp;
+  r.nq = nq;
+  r.g = r.row / nq;
+  r.cql = r.row - r.g * nq;
+  r.tl0 = lane % lpr;
+  r.tstep = lpr;
+  return r;
+}
+__device__ __forceinline__ void t2_next(RowIter& r) {
+  r.row += r.step;
+  r.cql += r.step;
+  while (r.cql >= r.nq) { r.cql -= r.nq; ++r.g; }
+}
 
 struct TileCoord {
   int mtile, b0, nsamp, t0, tw;
@@ -260,7 +284,7 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
           sx[(size_t)q * a.srows + g * a.R + u] = v;
           wrote = true;
         }
-        if (wrote) tc::fence_proxy_async_smem();   // only writers pay for the proxy fence
+        if (wrote && !(a.variant & 4)) tc::fence_proxy_async_smem();   // only writers pay for the proxy fence (bit 2: timing experiment, WRONG results)
         tc::mbar_arrive(&bar_ready[s]);
         if (a.dbg) dbg1 += clock64() - w1;
         if (++s == a.nstage) { s = 0; ph ^= 1u; }
@@ -286,6 +310,12 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
     const int ots = d.out_tstride > 0 ? d.out_tstride : 1, oto = d.out_toff;
     const int sshift = S == 2 ? 1 : 0, smask = sshift;
     const bool fold = (d.flags & AVC_F_FOLD) != 0;
+    // AVC_F_NORMBWD (with AVC_F_FOLD): norm / relu / eps / cond / save_c / stats / dc / dcond / dbias describe the UPSTREAM
+    // block whose output gradient this data-gradient conv produces; its InstanceNorm/AdaIN/ReLU backward runs here
+    const bool nbw = fold && (d.flags & AVC_F_NORMBWD) != 0;
+    const bool fwd_norm = d.norm && !nbw;
+    float* dbacc = par;   // [128] per-CTA bias-gradient partial sums of the upstream block (nbw, upstream without norm)
+    if (nbw && d.dbias && etid < 128) par[etid] = 0.f;   // ordered before the first use by the barriers of the first tile
     const int fpl = (d.flags >> 8) & 0xff, fpr = (d.flags >> 16) & 0xff;
     const bool rnd_out = (d.flags & AVC_F_ROUND_OUT) != 0;
     bool ok = true;
@@ -320,19 +350,31 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
               if (k == 1 && !two) break;
+              const int cbase = 16 * (j + 2 * k);
+              if (S == 1 && cbase + 16 <= ncol) {   // whole chunk valid, stride 1: no per-column predicates
+                float* sd = sdst + (size_t)cbase * 4;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int col = 16 * (j + 2 * k) + i;
-                if (col < ncol && (col & smask) == 0) {
+                for (int i = 0; i < 16; ++i) {
                   const float x = v[16 * k + i] + bias;
                   s1 += x;
                   s2 = fmaf(x, x, s2);
-                  sdst[(size_t)(col >> sshift) * 4] = x;
+                  sd[i * 4] = x;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const int col = cbase + i;
+                  if (col < ncol && (col & smask) == 0) {
+                    const float x = v[16 * k + i] + bias;
+                    s1 += x;
+                    s2 = fmaf(x, x, s2);
+                    sdst[(size_t)(col >> sshift) * 4] = x;
+                  }
                 }
               }
             }
           }
-          if (d.norm) stat[(half * a.G + g) * 128 + col_l] = make_float2(s1, s2);
+          if (fwd_norm) stat[(half * a.G + g) * 128 + col_l] = make_float2(s1, s2);
         }
       }
       if (a.variant) tc::fence_proxy_async_smem();   // the staged rows will be read by bulk (async-proxy) stores
@@ -341,7 +383,7 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
       const long long e2 = a.dbg ? clock64() : 0;
       t2_bar_sync(2, 256);
       // ---------------- per (sample, channel) parameters: mean, scale = rstd*gamma, shift = beta
-      for (int g = half; g < c.nsamp; g += 2) {
+      for (int g = half; g < c.nsamp && !fold; g += 2) {
         const int b = c.b0 + g;
         float mean = 0.f, rstd = 1.f;
         const int cn = shuf ? co >> 1 : co;
@@ -381,13 +423,30 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
           // D holds Tout = T + pl + pr columns of the zero-padded transposed conv; dx[t] = D[t+pl]
           // + D[pl-t] (1 <= t <= pl) + D[2(T-1)-t+pl] (t >= T-1-pr, t <= T-2) + residual adjoint
           const int Tf = d.Tout - fpl - fpr;
-          for (int row = ewarp; row < c.nsamp * nq; row += 8) {
-            const int g = row / nq, cql = row - g * nq;
+          RowIter ri;   // (g, cql) walk: per-sample base pointers, per-row pointer = base + row * stride
+          ri.tstep = Tf <= 16 ? 16 : 32;
+          ri.tl0 = lane % ri.tstep;
+          const int frpp = 32 / ri.tstep, fsub = lane / ri.tstep;
+          for (int g = 0; g < c.nsamp; ++g)
+          for (int cql = ewarp * frpp + fsub; cql < nq; cql += 8 * frpp) {
             const int b = c.b0 + g, cq = c.mtile * 32 + cql;
             const float4* sr = st4p + (size_t)cql * P + g * Ts;
-            float* ob = d.out + (size_t)b * d.out_bstride + ((size_t)cq * Tf) * 4;
+            float* ob = d.out ? d.out + (size_t)b * d.out_bstride + ((size_t)cq * Tf) * 4 : nullptr;
             const float* rb = d.res ? d.res + (size_t)b * d.res_bstride + ((size_t)cq * d.res_T) * 4 : nullptr;
-            for (int t = lane; t < Tf; t += 32) {
+            // upstream block (nbw): its raw conv output c, statistics and AdaIN row for these 4 channels
+            const float* ucb = nbw ? d.save_c + (((size_t)b * (d.Cout >> 2) + cq) * Tf) * 4 : nullptr;
+            float4 um = zero4(), ur = make_float4(1.f, 1.f, 1.f, 1.f), ub = zero4(), ug = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (nbw && d.norm) {
+              const float4 s01 = ldg4(d.stats + ((size_t)b * d.Cout + cq * 4) * 2), s23 = ldg4(d.stats + ((size_t)b * d.Cout + cq * 4) * 2 + 4);
+              um = make_float4(s01.x, s01.z, s23.x, s23.z);
+              ur = make_float4(s01.y, s01.w, s23.y, s23.w);
+              if (d.cond) {
+                ub = ldg4(d.cond + (size_t)b * d.cond_bstride + cq * 4);
+                ug = ldg4(d.cond + (size_t)b * d.cond_bstride + d.Cout + cq * 4);
+              }
+            }
+            float4 a0 = zero4(), a1 = zero4();   // sum of g, sum of g * xhat over the row (this lane's share)
+            for (int t = ri.tl0; t < Tf; t += ri.tstep) {
               float4 o = sr[t + fpl];
               if (t >= 1 && t <= fpl) {
                 const float4 m = sr[fpl - t];
@@ -412,24 +471,149 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
                 }
                 o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
               }
-              st4(ob + (size_t)t * 4, o);
+              if (ob) st4(ob + (size_t)t * 4, o);
+              if (nbw) {
+                // first half of the upstream norm backward: ReLU mask, row sums; the masked gradient goes back into
+                // the staged tile (column t + fpl is read by this lane only)
+                const float4 c4 = ldg4(ucb + (size_t)t * 4);
+                float4 xh = c4, pre = c4;
+                if (d.norm) {
+                  xh = make_float4((c4.x - um.x) * ur.x, (c4.y - um.y) * ur.y, (c4.z - um.z) * ur.z, (c4.w - um.w) * ur.w);
+                  pre = make_float4(fmaf(xh.x, ug.x, ub.x), fmaf(xh.y, ug.y, ub.y), fmaf(xh.z, ug.z, ub.z), fmaf(xh.w, ug.w, ub.w));
+                }
+                if (d.relu) {
+                  o.x = pre.x > 0.f ? o.x : 0.f; o.y = pre.y > 0.f ? o.y : 0.f; o.z = pre.z > 0.f ? o.z : 0.f; o.w = pre.w > 0.f ? o.w : 0.f;
+                }
+                a0.x += o.x; a0.y += o.y; a0.z += o.z; a0.w += o.w;
+                a1.x = fmaf(o.x, xh.x, a1.x); a1.y = fmaf(o.y, xh.y, a1.y); a1.z = fmaf(o.z, xh.z, a1.z); a1.w = fmaf(o.w, xh.w, a1.w);
+                const_cast<float4*>(sr)[t + fpl] = o;
+              }
+            }
+            if (nbw) {
+              // row sums across the lanes of this row (16 or 32 lanes)
+#pragma unroll
+              for (int off = 16; off > 0; off >>= 1) {
+                if (off < ri.tstep) {
+                  a0.x += __shfl_xor_sync(0xffffffffu, a0.x, off); a0.y += __shfl_xor_sync(0xffffffffu, a0.y, off);
+                  a0.z += __shfl_xor_sync(0xffffffffu, a0.z, off); a0.w += __shfl_xor_sync(0xffffffffu, a0.w, off);
+                  a1.x += __shfl_xor_sync(0xffffffffu, a1.x, off); a1.y += __shfl_xor_sync(0xffffffffu, a1.y, off);
+                  a1.z += __shfl_xor_sync(0xffffffffu, a1.z, off); a1.w += __shfl_xor_sync(0xffffffffu, a1.w, off);
+                }
+              }
+              if (d.norm && d.dcond && ri.tl0 == 0) {   // AdaIN row gradients: d beta = sum g, d gamma = sum g * xhat
+                st4(d.dcond + (size_t)b * d.dcond_bstride + cq * 4, a0);
+                st4(d.dcond + (size_t)b * d.dcond_bstride + d.Cout + cq * 4, a1);
+              }
+              const float invT = 1.f / (float)Tf;
+              const float4 m0 = make_float4(a0.x * invT, a0.y * invT, a0.z * invT, a0.w * invT);
+              const float4 m1 = make_float4(a1.x * invT, a1.y * invT, a1.z * invT, a1.w * invT);
+              const float4 k = make_float4(ur.x * ug.x, ur.y * ug.y, ur.z * ug.z, ur.w * ug.w);
+              float* dcb = d.dc + (((size_t)b * (d.Cout >> 2) + cq) * Tf) * 4;
+              float4 db = zero4();
+              __syncwarp();
+              for (int t = ri.tl0; t < Tf; t += ri.tstep) {
+                float4 gq = sr[t + fpl];
+                if (d.norm) {
+                  const float4 c4 = ldg4(ucb + (size_t)t * 4);
+                  const float4 xh = make_float4((c4.x - um.x) * ur.x, (c4.y - um.y) * ur.y, (c4.z - um.z) * ur.z, (c4.w - um.w) * ur.w);
+                  gq = make_float4(k.x * (gq.x - m0.x - xh.x * m1.x), k.y * (gq.y - m0.y - xh.y * m1.y), k.z * (gq.z - m0.z - xh.z * m1.z),
+                                   k.w * (gq.w - m0.w - xh.w * m1.w));
+                }
+                db.x += gq.x; db.y += gq.y; db.z += gq.z; db.w += gq.w;
+                if (rnd_out) gq = t2_round4(gq);
+                st4(dcb + (size_t)t * 4, gq);
+              }
+              if (d.dbias) {   // upstream bias gradient: per-CTA partial sums in shared memory, flushed once at the end
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                  if (off < ri.tstep) {
+                    db.x += __shfl_xor_sync(0xffffffffu, db.x, off); db.y += __shfl_xor_sync(0xffffffffu, db.y, off);
+                    db.z += __shfl_xor_sync(0xffffffffu, db.z, off); db.w += __shfl_xor_sync(0xffffffffu, db.w, off);
+                  }
+                }
+                if (ri.tl0 == 0) {
+                  atomicAdd(dbacc + cql * 4 + 0, db.x); atomicAdd(dbacc + cql * 4 + 1, db.y);
+                  atomicAdd(dbacc + cql * 4 + 2, db.z); atomicAdd(dbacc + cql * 4 + 3, db.w);
+                }
+              }
             }
           }
+        } else if (!shuf && !d.mask && ots == 1 && a.variant == 0) {
+          // Common case (every block without pixel shuffle / mask): `c` and `out` in ONE sweep over the staged tile.
+          // Per-sample base pointers, per-row pointer = base + row * stride, four time steps per lane in flight:
+          // the per-row 64-bit address arithmetic of the generic loops below was a ~300-cycle dependent chain in
+          // front of every store with only two epilogue warps per scheduler to hide it.
+          const int lpr = c.tw <= 16 ? 16 : 32, rpp = 32 / lpr, sub = lane / lpr, tl0 = lane - sub * lpr;
+          for (int g = 0; g < c.nsamp; ++g) {
+            const int b = c.b0 + g;
+            float* ob_g = d.out + (size_t)b * d.out_bstride + ((size_t)(c.mtile * 32) * out_T + c.t0 + oto) * 4;
+            float* cb_g = d.save_c ? d.save_c + (((size_t)b * (d.Cout >> 2) + c.mtile * 32) * d.Tout + c.t0) * 4 : nullptr;
+            const float* rb_g = d.res ? d.res + (size_t)b * d.res_bstride + ((size_t)(c.mtile * 32) * d.res_T) * 4 : nullptr;
+            const float4* sr_g = st4p + g * Ts;
+            for (int cql = ewarp * rpp + sub; cql < nq; cql += 8 * rpp) {
+              const float4 mean4 = par4[(0 * a.G + g) * 32 + cql], sc4 = par4[(1 * a.G + g) * 32 + cql], sh4 = par4[(2 * a.G + g) * 32 + cql];
+              const float4* sr = sr_g + (size_t)cql * P;
+              float* ob = ob_g + (size_t)cql * out_T * 4;
+              float* cb = cb_g ? cb_g + (size_t)cql * d.Tout * 4 : nullptr;
+              const float* rb = rb_g ? rb_g + (size_t)cql * d.res_T * 4 : nullptr;
+              for (int tb = tl0; tb < c.tw; tb += 4 * lpr) {
+                float4 x[4], r[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const int tl_ = tb + k * lpr;
+                  x[k] = tl_ < c.tw ? sr[tl_] : zero4();
+                  r[k] = zero4();
+                }
+                if (rb) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const int tl_ = tb + k * lpr, t = c.t0 + tl_;
+                    if (tl_ < c.tw) {
+                      if (d.res_mode == AVC_RES_SAME) r[k] = ldg4(rb + (size_t)t * 4);
+                      else if (d.res_mode == AVC_RES_UP) r[k] = ldg4(rb + (size_t)(t >> 1) * 4);
+                      else {
+                        r[k] = ldg4(rb + (size_t)(2 * t) * 4);
+                        if (2 * t + 1 < d.res_T) {
+                          const float4 r2 = ldg4(rb + (size_t)(2 * t + 1) * 4);
+                          r[k] = make_float4(0.5f * (r[k].x + r2.x), 0.5f * (r[k].y + r2.y), 0.5f * (r[k].z + r2.z), 0.5f * (r[k].w + r2.w));
+                        }
+                      }
+                    }
+                  }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const int tl_ = tb + k * lpr;
+                  if (tl_ < c.tw) {
+                    if (cb) st4(cb + (size_t)tl_ * 4, x[k]);
+                    float4 o;
+                    o.x = fmaf(x[k].x - mean4.x, sc4.x, sh4.x); o.y = fmaf(x[k].y - mean4.y, sc4.y, sh4.y);
+                    o.z = fmaf(x[k].z - mean4.z, sc4.z, sh4.z); o.w = fmaf(x[k].w - mean4.w, sc4.w, sh4.w);
+                    if (d.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    o.x += r[k].x; o.y += r[k].y; o.z += r[k].z; o.w += r[k].w;
+                    if (rnd_out) o = t2_round4(o);
+                    st4(ob + (size_t)tl_ * 4, o);
+                  }
+                }
+              }
+            }
+          }
+          if (a.dbg) e3b = clock64();
         } else {
           const bool bulk_c = (a.variant & 1) != 0;
           const bool bulk_y = (a.variant & 2) != 0 && !shuf && ots == 1;
           if (d.save_c) {  // raw conv (+bias) rows in conv layout, kept for the backward pass
-            for (int row = ewarp; row < c.nsamp * nq; row += 8) {
-              const int g = row / nq, cql = row - g * nq;
+            for (RowIter ri = t2_rows(ewarp, lane, c.tw, nq); ri.row < c.nsamp * nq; t2_next(ri)) {
+              const int g = ri.g, cql = ri.cql;
               const float4* sr = st4p + (size_t)cql * P + g * Ts;
               float* cb = d.save_c + (((size_t)(c.b0 + g) * (d.Cout >> 2) + (c.mtile * 32 + cql)) * d.Tout + c.t0) * 4;
               if (bulk_c) {   // one bulk (TMA) store per row: the copy engine moves it, no LSU traffic
-                if (lane == 0) tc::bulk_s2g(cb, sr, (uint32_t)c.tw * 16u);
+                if (ri.tl0 == 0) tc::bulk_s2g(cb, sr, (uint32_t)c.tw * 16u);
               } else {
-                for (int t = lane; t < c.tw; t += 32) st4(cb + (size_t)t * 4, sr[t]);
+                for (int t = ri.tl0; t < c.tw; t += ri.tstep) st4(cb + (size_t)t * 4, sr[t]);
               }
             }
-            if (bulk_c && lane == 0) {
+            if (bulk_c) {
               tc::bulk_commit();
               if (bulk_y) tc::bulk_wait_read_all();   // the rows are about to be overwritten in place
             }
@@ -439,8 +623,8 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
           const int nqo = shuf ? nq >> 1 : nq;       // output chunks of this tile
           const int two = shuf ? c.tw * 2 : c.tw;    // output time steps of this tile
           const int to0 = shuf ? c.t0 * 2 : c.t0;    // first output time step of this tile
-          for (int row = ewarp; row < c.nsamp * nqo; row += 8) {
-            const int g = row / nqo, cql = row - g * nqo;
+          for (RowIter ri = t2_rows(ewarp, lane, two, nqo); ri.row < c.nsamp * nqo; t2_next(ri)) {
+            const int g = ri.g, cql = ri.cql;
             const int b = c.b0 + g;
             const int cqo = c.mtile * (shuf ? 16 : 32) + cql;
             float* ob = d.out + (size_t)b * d.out_bstride + ((size_t)cqo * out_T) * 4;
@@ -465,7 +649,7 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
               srA = st4p + (size_t)(2 * cql) * P + g * Ts;
               srB = st4p + (size_t)(2 * cql + 1) * P + g * Ts;
             }
-            for (int tl_ = lane; tl_ < two; tl_ += 32) {
+            for (int tl_ = ri.tl0; tl_ < two; tl_ += ri.tstep) {
               float4 x;
               if (!shuf) {
                 x = srA[tl_];
@@ -502,10 +686,10 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
             if (bulk_y) {
               tc::fence_proxy_async_smem();
               __syncwarp();
-              if (lane == 0) tc::bulk_s2g(ob + (size_t)(to0 + oto) * 4, srA, (uint32_t)two * 16u);
+              if (ri.tl0 == 0) tc::bulk_s2g(ob + (size_t)(to0 + oto) * 4, srA, (uint32_t)two * 16u);
             }
           }
-          if ((bulk_c || bulk_y) && lane == 0) {
+          if (bulk_c || bulk_y) {
             tc::bulk_commit();
             tc::bulk_wait_read_all();   // the staged tile is rewritten by the next tile's TMEM pass
           }
@@ -519,6 +703,7 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
         dbg0 += e1 - e0; dbg1 += e2 - e1; dbg2 += e3 - e2; dbg3 += e3b - e3; dbg4 += e3c - e3b; dbg5 += e4 - e3c;
       }
     }
+    if (nbw && d.dbias && etid < 128 && etid < d.Cout && tl > 0) atomicAdd(d.dbias + etid, dbacc[etid]);   // mtiles == 1 (plan)
     if (a.dbg && etid == 0) {
       long long* o = a.dbg + (size_t)blockIdx.x * 16;
       o[8] = dbg0; o[9] = dbg1; o[10] = dbg2; o[11] = dbg3; o[12] = tl; o[13] = dbg4; o[14] = dbg5;
@@ -556,6 +741,7 @@ int t2_plan(const avc_conv_desc* d, Tc2Args& a) {
   a.mtiles = cdiv(d->Cout, 128);
   const int ncol_full = (d->Tout - 1) * S + 1;
   if (d->pad_mode == AVC_PAD_REFLECT && d->Tin <= d->pad_left) return AVC_ERR_UNSUPPORTED;   // no mirror row to copy
+  if ((d->flags & AVC_F_NORMBWD) && (!fold || d->Cout > 128 || !d->save_c || !d->dc || (d->norm && !d->stats))) return AVC_ERR_UNSUPPORTED;
   if (d->in_bstride % 4 != 0 || ((uintptr_t)d->in & 15u)) return AVC_ERR_UNSUPPORTED;        // tensor-map strides are multiples of 16 bytes
   if (ncol_full <= 144) {
     a.TT = d->Tout;
@@ -609,16 +795,6 @@ int t2_plan(const avc_conv_desc* d, Tc2Args& a) {
   return AVC_OK;
 }
 
-typedef CUresult (*PFN_t2_encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-// the driver entry point is fetched through the runtime: the library does not link against libcuda
-static PFN_t2_encode t2_encode_fn() {
-  void* f = nullptr;
-  cudaDriverEntryPointQueryResult q;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
-  return (PFN_t2_encode)f;
-}
-
 static long long* g_tc2_dbg = nullptr;
 static int g_tc2_variant = -1;
 static int t2_variant() {
@@ -639,7 +815,7 @@ int conv_block_tc2_launch(const avc_conv_desc* d, int* status, void* stream) {
   a.variant = t2_variant();
   CUtensorMap tmx;
   {
-    static PFN_t2_encode enc = t2_encode_fn();
+    PFN_tmap_encode enc = tmap_encode_fn();
     if (!enc) {
       set_error("avc_conv_block_tc: cuTensorMapEncodeTiled is not available from this driver");
       return AVC_ERR_CUDA;

@@ -389,9 +389,12 @@ __global__ void __launch_bounds__(256) fold_add_kernel(const avc_fold_desc d) {
 }
 
 // grid (C/4 chunks, batch slices): block-reduce a slice of (b, t), one atomicAdd per channel
+// dbias_tab != null: channel group g = c / group_c accumulates into dbias_tab[g][c % group_c] (several layers whose dc
+// rows lie side by side in one tensor: the conv bank)
 __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ dc, int64_t bstride, float* __restrict__ dbias,
-                                                        int B, int C, int T, int bps) {
+                                                        int B, int C, int T, int bps, float* const* __restrict__ dbias_tab, int group_c) {
   const int q = blockIdx.x;
+  if (dbias_tab) dbias = dbias_tab[(q * 4) / group_c] - ((q * 4) / group_c) * group_c;
   const int b0 = blockIdx.y * bps, b1 = min(B, b0 + bps);
   float4 s = zero4();
   const int64_t n = (int64_t)(b1 - b0) * T;
@@ -467,7 +470,20 @@ extern "C" int avc_bias_grad(const float* dc, int64_t bstride, float* dbias, int
   if (slices < 1) slices = 1;
   const int bps = cdiv(B, slices);
   dim3 grid(C / 4, cdiv(B, bps));
-  AVC_LAUNCH(bias_grad_kernel, grid, 256, 0, (cudaStream_t)stream, dc, bstride, dbias, B, C, T, bps);
+  AVC_LAUNCH(bias_grad_kernel, grid, 256, 0, (cudaStream_t)stream, dc, bstride, dbias, B, C, T, bps, (float* const*)nullptr, 0);
   AVC_CHECK_LAUNCH("bias_grad");
+  return AVC_OK;
+}
+
+extern "C" int avc_bias_grad_groups(const float* dc, int64_t bstride, float* const* dbias_tab_dev, int group_c, int B, int C, int T, void* stream) {
+  AVC_REQUIRE(dc && dbias_tab_dev && B > 0 && C > 0 && C % 4 == 0 && T > 0 && group_c > 0 && group_c % 4 == 0 && C % group_c == 0, AVC_ERR_INVALID,
+              "avc_bias_grad_groups: bad argument");
+  int slices = cdiv(148 * 4, C / 4);
+  if (slices > B) slices = B;
+  if (slices < 1) slices = 1;
+  const int bps = cdiv(B, slices);
+  dim3 grid(C / 4, cdiv(B, bps));
+  AVC_LAUNCH(bias_grad_kernel, grid, 256, 0, (cudaStream_t)stream, dc, bstride, (float*)nullptr, B, C, T, bps, dbias_tab_dev, group_c);
+  AVC_CHECK_LAUNCH("bias_grad_groups");
   return AVC_OK;
 }

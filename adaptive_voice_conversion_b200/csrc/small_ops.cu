@@ -381,6 +381,7 @@ static Option g_opts[] = {
     {"tc_uniform_issue", "AVC_TC_ISSUE", "uniform", "legacy", AVC_DEFAULT_TC_UNIFORM_ISSUE, -1},
     {"wgrad_reduce_v2", "AVC_WGRAD_REDUCE", "v2", "v1", AVC_DEFAULT_WGRAD_REDUCE_V2, -1},
     {"tc_conv_v2", "AVC_TC_CONV", "v2", "v1", 1, -1},   // persistent conv block kernel (conv_tc2.cu); v1 = conv_tc.cu
+    {"wgrad_split", "AVC_WGRAD_KERNEL", "split", "r1", 0, -1},   // weight gradient with a dedicated MMA warp (conv_wgrad_split_kernel)
 };
 static int opt_value(int i) {
   Option& o = g_opts[i];
@@ -395,6 +396,7 @@ static int opt_value(int i) {
 int opt_tc_uniform_issue() { return opt_value(0); }
 int opt_wgrad_reduce_v2() { return opt_value(1); }
 int opt_tc_conv_v2() { return opt_value(2); }
+int opt_wgrad_split() { return opt_value(3); }
 }  // namespace avc
 extern "C" int avc_set_option(const char* name, int value) {
   if (name)

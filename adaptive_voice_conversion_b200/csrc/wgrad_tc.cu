@@ -251,6 +251,189 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_tc_kernel(const WgTcArgs a)
   if (warp == 0) tc::tmem_dealloc(tbase, (uint32_t)a.ncols_tmem);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Round-2 variant ("wgrad_split"): 8 staging / epilogue warps + a dedicated MMA warp, so that staging tile i+1 runs
+// under the MMAs of tile i (the kernel above issues from staging warp 0, whose blocking issue loop serialises the two:
+// 17.3 K staging + 16.6 K issue of a 43 K-cycle CTA, tools/diag_wgrad.py).  Pipelines: full[2] (256 staging arrivals),
+// free[2] (tcgen05.commit), done.  (Staging the operands with swizzled tensor-map TMA copies instead was tried and
+// dropped: CU_TENSOR_MAP_SWIZZLE_128B* needs 128-byte inner rows, the A4 layout has 16-byte ones.)
+constexpr int WS_STAGE_THREADS = 256;
+constexpr int WS_THREADS = WS_STAGE_THREADS + 32;
+
+template <bool ATOMIC>
+__global__ void __launch_bounds__(WS_THREADS, 1) conv_wgrad_split_kernel(const WgTcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_full[2], bar_free[2], bar_done;
+  __shared__ uint32_t tmem_slot;
+  const avc_wgrad_desc& d = a.d;
+  const int tid = threadIdx.x, warp = tc::warp_idx_sync(), lane = tid & 31;
+  const int ci0 = blockIdx.x * WT_NT, co0 = blockIdx.y * 128, sl = blockIdx.z;
+  const int K = d.K, T = d.Tout, TX = a.TX;
+  const int S = d.stride, H = a.H;
+  const int tile0 = sl * a.tiles_per_slice;
+  const int tile1 = min(cdiv(d.B, a.G), tile0 + a.tiles_per_slice);
+  if (tid == 0) {
+    tc::mbar_init(&bar_full[0], WS_STAGE_THREADS);
+    tc::mbar_init(&bar_full[1], WS_STAGE_THREADS);
+    tc::mbar_init(&bar_free[0], 1);
+    tc::mbar_init(&bar_free[1], 1);
+    tc::mbar_init(&bar_done, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 8) tc::tmem_alloc(&tmem_slot, (uint32_t)a.ncols_tmem);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  const uint32_t atomA = (uint32_t)a.RA * 128u, atomX = (uint32_t)a.RX * 128u;
+  const int nq_x = a.ntpad >> 2;
+  long long t_begin = 0, c_stage = 0, c_free = 0, c_issue = 0, q3 = 0, q4 = 0;
+  if (a.dbg) t_begin = clock64();
+  bool ok = true;
+
+  if (warp < 8) {
+    // ============================================================ staging warps: one tile of copies at a time; the
+    // tile is handed to the MMA warp as soon as its copies have landed, BEFORE waiting for the next free buffer
+    for (int tile = tile0; tile < tile1 && ok; ++tile) {
+      const int it = tile - tile0;
+      const int buf = it & 1;
+      const long long q0 = a.dbg ? clock64() : 0;
+      if (it >= 2) ok = tc::mbar_wait(&bar_free[buf], (uint32_t)((it >> 1) - 1) & 1u, a.status, 6);
+      const long long q1 = a.dbg ? clock64() : 0;
+      if (!ok) break;
+      uint8_t* sA = smem + (size_t)buf * a.buf_bytes;
+      uint8_t* sX = sA + a.x_off;
+      const int b0 = tile * a.G;
+      const int nsamp = min(a.G, d.B - b0);
+      for (int r = tid; r < nsamp * T; r += WS_STAGE_THREADS) {
+        const int g = r / T, t = r - g * T;
+        const float* src = d.dc + (size_t)(b0 + g) * d.dc_bstride + (size_t)t * 4;
+#pragma unroll 8
+        for (int q = 0; q < 32; ++q) {
+          const int co = co0 + 4 * q;
+          const bool cv = co < d.Cout;
+          cp_async16(sA + mn_unit_off(q, r, atomA), src + (size_t)((cv ? co : 0) >> 2) * T * 4, cv);
+        }
+      }
+      for (int r0 = tid; r0 < nsamp * TX; r0 += WS_STAGE_THREADS) {
+        const int g = r0 / TX, u = r0 - g * TX;
+        const int r = S == 1 ? r0 : g * 2 * H + (u & 1) * H + (u >> 1);
+        const int p = src_pos(u - d.pad_left, d.Tin, AVC_PAD_REFLECT, 1);
+        const float* src = d.x + (size_t)(b0 + g) * d.x_bstride + (size_t)(p >= 0 ? p : 0) * 4;
+#pragma unroll 8
+        for (int q = 0; q < nq_x; ++q) {
+          const int ci = ci0 + 4 * q;
+          const bool v = ci < d.Cin && p >= 0;
+          cp_async16(sX + mn_unit_off(q, r, atomX), src + (size_t)((v ? ci : 0) >> 2) * d.Tin * 4, v);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      tc::fence_proxy_async_smem();
+      tc::mbar_arrive(&bar_full[buf]);
+      if (a.dbg) {
+        const long long q2 = clock64();
+        c_free += q1 - q0;
+        c_stage += q2 - q1;
+      }
+    }
+  } else {
+    // ============================================================ MMA issuer (warp 8), uniform datapath
+    const uint32_t idesc = tc::make_idesc_tf32(128, a.ntpad, 1, 1);
+    const uint32_t tb_u = __shfl_sync(0xffffffffu, tbase, 0);
+    const uint32_t smem_base = __shfl_sync(0xffffffffu, tc::smem_u32(smem), 0);
+    const uint32_t hi = tc::sdesc_hi(512, 1);
+    const int nks = T >> 3;
+    for (int tile = tile0; tile < tile1 && ok; ++tile) {
+      const int it_u = tile - tile0;
+      const int nsamp_u = min(a.G, d.B - tile * a.G);
+      ok = __all_sync(0xffffffffu, tc::mbar_wait(&bar_full[it_u & 1], (uint32_t)(it_u >> 1) & 1u, a.status, 8));
+      if (!ok) break;
+      tc::tc_fence_after();
+      const long long q2 = a.dbg ? clock64() : 0;
+      const uint32_t sbase = smem_base + (uint32_t)(it_u & 1) * a.buf_bytes;
+      const uint32_t a_lo0 = tc::sdesc_lo(sbase, atomA), b_lo0 = tc::sdesc_lo(sbase + a.x_off, atomX);
+      for (int g = 0; g < nsamp_u; ++g) {
+        uint64_t a_desc = tc::sdesc64(a_lo0 + (uint32_t)(g * T) * 8u, hi);
+        uint64_t b_ks = tc::sdesc64(b_lo0 + (uint32_t)(S == 1 ? g * TX : g * 2 * H) * 8u, hi);
+        for (int ks = 0; ks < nks; ++ks) {
+          const uint32_t acc = (it_u | g | ks) ? 1u : 0u;
+          uint32_t dcol = tb_u;
+          if (S == 1) {
+            uint64_t b_desc = b_ks;
+            if (K == 5) {
+#pragma unroll
+              for (int j = 0; j < 5; ++j) {
+                tc::mma_tf32_elect(dcol, a_desc, b_desc, idesc, acc);
+                b_desc += 8u;
+                dcol += (uint32_t)a.ntpad;
+              }
+            } else {
+              for (int j = 0; j < K; ++j) {
+                tc::mma_tf32_elect(dcol, a_desc, b_desc, idesc, acc);
+                b_desc += 8u;
+                dcol += (uint32_t)a.ntpad;
+              }
+            }
+          } else {
+            for (int j = 0; j < K; ++j) {
+              tc::mma_tf32_elect(dcol, a_desc, b_ks + (uint32_t)((j & 1) * H + (j >> 1)) * 8u, idesc, acc);
+              dcol += (uint32_t)a.ntpad;
+            }
+          }
+          a_desc += 64u;
+          b_ks += 64u;
+        }
+      }
+      __syncwarp();
+      if (tc::elect_one()) tc::mma_commit(&bar_free[it_u & 1]);
+      __syncwarp();
+      if (a.dbg) c_issue += clock64() - q2;
+    }
+    __syncwarp();
+    if (tc::elect_one()) tc::mma_commit(&bar_done);
+  }
+  if (a.dbg) q3 = clock64();
+  ok = tc::mbar_wait(&bar_done, 0, a.status, 7) && ok;
+  ok = __syncthreads_and(ok) != 0;
+  tc::tc_fence_after();
+  if (a.dbg) q4 = clock64();
+  if (ok && tile1 > tile0 && warp < 8) {
+    const int quarter = warp & 3, half = warp >> 2;
+    const int co = co0 + quarter * 32 + lane;
+    const uint32_t lane_addr = tbase + ((uint32_t)(quarter * 32) << 16);
+    const int nch = a.ntpad >> 4;
+    for (int j = 0; j < K; ++j) {
+      float* sbase = a.scratch + (((size_t)(ATOMIC ? 0 : sl) * K + j) * (size_t)(d.Cin >> 2)) * (size_t)a.coutp * 4;
+      for (int ch = half; ch < nch; ch += 2) {
+        const int c0 = ch << 4;
+        float v[16];
+        tc::tmem_ld16(lane_addr + (uint32_t)(j * a.ntpad + c0), v);
+#pragma unroll
+        for (int i4 = 0; i4 < 16; i4 += 4) {
+          const int ci = ci0 + c0 + i4;
+          if (ci < d.Cin) {
+            float* p = sbase + ((size_t)(ci >> 2) * a.coutp + co) * 4;
+            if constexpr (ATOMIC)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[i4]), "f"(v[i4 + 1]), "f"(v[i4 + 2]), "f"(v[i4 + 3]) : "memory");
+            else
+              st4(p, make_float4(v[i4], v[i4 + 1], v[i4 + 2], v[i4 + 3]));
+          }
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (a.dbg && (tid == 0 || tid == WS_STAGE_THREADS)) {
+    long long* o = a.dbg + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8;
+    const long long q5 = clock64();
+    if (tid == 0) { o[0] = t_begin; o[1] = q5; o[2] = c_stage; o[3] = c_free; o[5] = q4 - q3; o[6] = q5 - q4; o[7] = tile1 - tile0; }
+    else o[4] = c_issue;
+  }
+  if (warp == 8) tc::tmem_dealloc(tbase, (uint32_t)a.ncols_tmem);
+}
+
 // dW[co][ci][j] += sum over slices of scratch[sl][j][ci/4][co][ci%4]
 // block (32, 8): x = output float4 (coalesced 512 B per warp), y = slice group
 template <bool V2>
@@ -294,23 +477,38 @@ __global__ void __launch_bounds__(256) wgrad_tc_reduce_kernel(const float* __res
   }
 }
 
-// dW[co][ci][j] += acc[j][ci/4][co][ci%4]; acc = 0.   grid.y = layer (device item table), grid.x
-// covers the largest layer (smaller layers exit early)
+// dW[co][ci][j] += acc[j][ci/4][co][ci%4]; acc = 0.   grid.y = layer (device item table), grid.x covers the largest
+// layer (surplus blocks exit).  A block moves a 32 co x 32 ci x K tile through shared memory so that BOTH sides are
+// coalesced: 512-byte runs of the accumulation buffer in, (32 ci x K)-float runs of the nn.Conv1d gradient out.  (Round
+// 1 wrote the gradient with a 4-byte scatter at stride K: 209 us per step, now the kernel is copy-bound.)
 __global__ void __launch_bounds__(256) wgrad_acc_flush_kernel(const avc_wgrad_acc_item* __restrict__ items) {
+  __shared__ float tile[32][32 * 8 + 1];
   const avc_wgrad_acc_item it = items[blockIdx.y];
+  const int K = it.K, C4 = it.Cin >> 2;
   const int coutp = cdiv(it.Cout, 128) * 128;
-  const int64_t n = (int64_t)it.K * (it.Cin >> 2) * coutp;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float4* a4 = reinterpret_cast<float4*>(it.acc) + i;
-  const float4 s = *a4;
-  *a4 = zero4();
-  const int co = (int)(i % coutp);
-  if (co < it.Cout) {
-    const int64_t r = i / coutp;
-    const int c4 = (int)(r % (it.Cin >> 2)), j = (int)(r / (it.Cin >> 2));
-    float* o = it.dw + ((int64_t)co * it.Cin + c4 * 4) * it.K + j;
-    o[0] += s.x; o[it.K] += s.y; o[2 * it.K] += s.z; o[3 * it.K] += s.w;
+  const int ncg = cdiv(C4, 8);                      // groups of 8 four-channel chunks (32 input channels)
+  const int nblk = (coutp >> 5) * ncg;
+  if ((int)blockIdx.x >= nblk) return;
+  const int cot = blockIdx.x / ncg, cg = blockIdx.x - cot * ncg;
+  const int co0 = cot << 5, c40 = cg << 3;
+  const int tid = threadIdx.x, col = tid & 31, c4l = tid >> 5;
+  if (c40 + c4l < C4) {
+    for (int j = 0; j < K; ++j) {
+      float4* a4 = reinterpret_cast<float4*>(it.acc) + ((size_t)j * C4 + c40 + c4l) * coutp + co0 + col;
+      const float4 s = *a4;
+      *a4 = zero4();
+      float* t = &tile[col][(c4l * 4) * K + j];
+      t[0] = s.x; t[K] = s.y; t[2 * K] = s.z; t[3 * K] = s.w;
+    }
+  }
+  __syncthreads();
+  const int nci = min(32, it.Cin - c40 * 4);         // input channels of this tile
+  const int run = nci * K;                            // contiguous floats of one output-channel row
+  for (int r = tid >> 5; r < 32; r += 8) {
+    const int co = co0 + r;
+    if (co >= it.Cout) break;
+    float* o = it.dw + ((size_t)co * it.Cin + c40 * 4) * K;
+    for (int e = tid & 31; e < run; e += 32) o[e] += tile[r][e];
   }
 }
 
@@ -325,7 +523,9 @@ static int wgrad_tc_plan(const avc_wgrad_desc* d, WgTcArgs& a) {
   a.H = ((a.TX + 1) / 2 + 3) / 4 * 4;
   // atom stride must keep every atom base 512 B aligned: the swizzle XOR is keyed on absolute
   // shared-memory address bits [7,9)
-  a.RX = d->stride == 1 ? (a.G * a.TX + 3) / 4 * 4 : a.G * 2 * a.H;
+  // (and 1024 B aligned for the tensor-map copies of the TMA-staged kernel: a swizzled destination must sit on the
+  // swizzle pattern's 8-row period)
+  a.RX = d->stride == 1 ? (a.G * a.TX + 7) / 8 * 8 : a.G * 2 * a.H;
   a.ntpad = WT_NT;
   a.coutp = cdiv(d->Cout, 128) * 128;
   int ncols = 32;
@@ -383,9 +583,24 @@ static int wgrad_tc_launch(const avc_wgrad_desc* d, float* scratch, int* status,
     attr_done = true;
   }
   dim3 grid(cdiv(d->Cin, WT_NT), cdiv(d->Cout, 128), a.nslices);
-  void (*kern)(const WgTcArgs) = opt_tc_uniform_issue() ? conv_wgrad_tc_kernel<true, false> : conv_wgrad_tc_kernel<false, false>;
-  if (accumulate) kern = conv_wgrad_tc_kernel<true, true>;
-  AVC_LAUNCH(kern, grid, 128, smem, (cudaStream_t)stream, a);
+  if (opt_wgrad_split()) {   // "wgrad_split": dedicated MMA warp
+    static bool attr2 = false;
+    if (!attr2) {
+      cudaError_t e = cudaFuncSetAttribute(conv_wgrad_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_wgrad_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+      if (e != cudaSuccess) {
+        set_error("%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e));
+        return AVC_ERR_CUDA;
+      }
+      attr2 = true;
+    }
+    if (accumulate) AVC_LAUNCH(conv_wgrad_split_kernel<true>, grid, WS_THREADS, smem, (cudaStream_t)stream, a);
+    else AVC_LAUNCH(conv_wgrad_split_kernel<false>, grid, WS_THREADS, smem, (cudaStream_t)stream, a);
+  } else {
+    void (*kern)(const WgTcArgs) = opt_tc_uniform_issue() ? conv_wgrad_tc_kernel<true, false> : conv_wgrad_tc_kernel<false, false>;
+    if (accumulate) kern = conv_wgrad_tc_kernel<true, true>;
+    AVC_LAUNCH(kern, grid, 128, smem, (cudaStream_t)stream, a);
+  }
   AVC_CHECK_LAUNCH(who);
   if (accumulate) return AVC_OK;
   const int64_t n = (int64_t)d->K * (d->Cin / 4) * a.coutp;
@@ -413,7 +628,9 @@ extern "C" int avc_conv_wgrad_tc_acc(const avc_wgrad_desc* d, float* acc, int* s
 }
 extern "C" int avc_wgrad_acc_flush(const avc_wgrad_acc_item* items_dev, int n_items, int64_t max_units, void* stream) {
   AVC_REQUIRE(items_dev && n_items > 0 && max_units > 0, AVC_ERR_INVALID, "avc_wgrad_acc_flush: bad argument");
-  dim3 grid((unsigned)cdiv64(max_units, 256), (unsigned)n_items);
+  // a layer needs (coutp / 32) * ceil(Cin / 32) blocks <= units / (256 K) + coutp / 32: max_units / 256 plus a margin
+  // covers every layer (surplus blocks exit at once)
+  dim3 grid((unsigned)cdiv64(max_units, 256) + 64u, (unsigned)n_items);
   AVC_LAUNCH(wgrad_acc_flush_kernel, grid, 256, 0, (cudaStream_t)stream, items_dev);
   AVC_CHECK_LAUNCH("wgrad_acc_flush");
   return AVC_OK;

@@ -106,6 +106,9 @@ class Engine:
         self.fold_fused = os.environ.get("AVC_FOLD_FUSED", "1" if L.DEFAULT_FOLD_FUSED else "0") == "1"
         self._wg_acc = None
         self.tc_conv_v2 = bool(self.lib.avc_get_option(b"tc_conv_v2"))
+        # the data-gradient conv of a block also runs the upstream block's norm backward (AVC_F_NORMBWD); off = one
+        # avc_norm_bwd launch per block
+        self.norm_bwd_fused = os.environ.get("AVC_NORM_BWD_FUSED", "1" if L.DEFAULT_NORM_BWD_FUSED else "0") == "1"
         # diagnostic (tools/diag_tf32.py, tests/test_gpu_tf32_accuracy.py): forward conv blocks on the exact-fp32 FFMA
         # kernels while the backward stays on the tensor cores -- separates "TF32 forward flips ReLU masks" from
         # "TF32 backward kernels are inaccurate" in the gradient-parity numbers
@@ -154,9 +157,21 @@ class Engine:
     def _param_table(self, kind: str, names, D: Dict[str, torch.Tensor]) -> torch.Tensor:
         return self._ptr_table((kind, names[0]), [D[n + sfx] for n in names for sfx in (".weight", ".bias")])
 
+    def _bank_bias_table(self, enc, nb, G):
+        """Device table of the nb conv-bank bias-gradient pointers (avc_bias_grad_groups); None when the bank's
+        biases are not all in G (a partial parameter set in tests)."""
+        names = [f"{enc}.conv_bank.{i}.bias" for i in range(nb)]
+        if not all(n in G for n in names):
+            return None
+        return self._ptr_table(("bank_bias", enc), [G[n] for n in names])
+
     def prepare_tables(self, P, G=None):
         """Build the device pointer tables of the fused dense paths NOW (a host-to-device copy):
         they must exist before a CUDA-graph capture, which cannot contain that copy."""
+        if G is not None:
+            for enc, key in (("speaker_encoder", "SpeakerEncoder"), ("content_encoder", "ContentEncoder")):
+                c = self.cfg[key]
+                self._bank_bias_table(enc, len(range(c["bank_scale"], c["bank_size"] + 1, c["bank_scale"])), G)
         if not self.fused_dense:
             return
         for names in (self._dense_names(), self._affine_names()):
@@ -416,15 +431,39 @@ class Engine:
             d.res, d.res_bstride, d.res_mode, d.res_T = res.ptr, res.bstride, res_mode, res.T
         d.stats = _ptr(stats)
 
-    def conv_bwd(self, P, G, rec, dy: A4, *, need_dx=True, dres: Optional[A4] = None, dres_mode=L.RES_NONE,
-                 dcond: Optional[torch.Tensor] = None, mask: Optional[A4] = None, dx_channels=None) -> Optional[A4]:
+    def _can_fuse_norm_bwd(self, rec, up, Cdx) -> bool:
+        """May the data-gradient conv of `rec` run the InstanceNorm/AdaIN/ReLU backward of the upstream block `up`
+        in its own epilogue (AVC_F_NORMBWD)?  Needs the persistent kernel's fold path and matching shapes."""
+        if not (self.norm_bwd_fused and self.fold_fused and self.tc_conv_v2 and self.precision == "tf32") or up is None:
+            return False
+        xin, K, pl, pr = rec["xin"], rec["K"], rec["pl"], rec["pr"]
+        Lp = xin.T + pl + pr
+        if not (rec["stride"] == 1 and K > 1 and rec["Cout"] % 16 == 0 and Lp <= 144 and "dgrad_tc" in self.packed[rec["name"]]
+                and xin.T >= 2 * pl + 1 and xin.T >= pr + 2):
+            return False
+        return (not up["shuffle"] and up["c"] is not None and (up["norm"] or up["relu"]) and up["Cout"] == Cdx and Cdx <= 128
+                and up["Tout"] == xin.T)
+
+    def conv_bwd(self, P, G, rec, dy: Optional[A4], *, need_dx=True, dres: Optional[A4] = None, dres_mode=L.RES_NONE,
+                 dcond: Optional[torch.Tensor] = None, mask: Optional[A4] = None, dx_channels=None,
+                 dc_pre: Optional[A4] = None, fuse_up: Optional[dict] = None) -> Optional[A4]:
         """Backward of one conv block.  dy: grad w.r.t. the block output *before* the residual
-        add.  Returns grad w.r.t. the block input (+ adjoint of the residual branch `dres`)."""
+        add.  Returns grad w.r.t. the block input (+ adjoint of the residual branch `dres`).
+
+        dc_pre: the gradient w.r.t. this block's raw conv output, already produced by the downstream block's fused
+        epilogue (then dy is ignored).  fuse_up = {"rec": upstream block, "dcond": its AdaIN-row gradient or None,
+        "need_dx": bool}: if eligible, this block's data-gradient conv also runs the upstream block's norm backward;
+        fuse_up["dc"] then holds the upstream dc (pass it as dc_pre to the upstream conv_bwd) and the return value is
+        None unless need_dx."""
         name, xin, B = rec["name"], rec["xin"], rec["xin"].B
         K, Cin, Cout, Tout, stride = rec["K"], rec["Cin"], rec["Cout"], rec["Tout"], rec["stride"]
         st = self.stream
         gb = G[name + ".bias"]
-        if rec["norm"] or rec["relu"]:
+        if fuse_up is not None:
+            fuse_up["dc"] = None
+        if dc_pre is not None:
+            dc = dc_pre
+        elif rec["norm"] or rec["relu"]:
             dc = A4.empty(B, Cout, Tout, self.dev)
             d = L.ConvDesc()
             d.B, d.Cin, d.Cout, d.K, d.stride, d.Tin, d.Tout = B, Cin, Cout, K, stride, xin.T, Tout
@@ -492,6 +531,26 @@ class Engine:
                 d.flags = int(d.flags) | L.F_FOLD | (rec["pl"] << 8) | (rec["pr"] << 16)
                 if dres is not None:
                     d.res, d.res_bstride, d.res_mode, d.res_T = dres.ptr, dres.bstride, dres_mode, dres.T
+                up = fuse_up["rec"] if fuse_up is not None else None
+                if up is not None and mask is None and self._can_fuse_norm_bwd(rec, up, Cdx):
+                    # ... and the upstream block's InstanceNorm / AdaIN / ReLU backward (avc_norm_bwd's job)
+                    dc_up = A4.empty(B, Cdx, xin.T, self.dev)
+                    dc_up.tf32 = True
+                    d.flags = int(d.flags) | L.F_NORMBWD | L.F_ROUND_OUT
+                    d.norm, d.relu, d.eps = int(up["norm"]), int(up["relu"]), IN_EPS
+                    d.save_c, d.stats = up["c"].ptr, _ptr(up["stats"])
+                    if up["cond"] is not None:
+                        d.cond, d.cond_bstride = up["cond"].data_ptr(), up["cond"].stride(0)
+                        d.dcond, d.dcond_bstride = fuse_up["dcond"].data_ptr(), fuse_up["dcond"].stride(0)
+                    d.dc = dc_up.ptr
+                    d.dbias = None if up["norm"] else G[up["name"] + ".bias"].data_ptr()
+                    if not fuse_up.get("need_dx", True):
+                        d.out = None
+                    self._ck(self.lib.avc_conv_block_tc(C.byref(d), self.tc_status.data_ptr(), st), f"conv_dgrad_tc_fold_normbwd[{name}]")
+                    fuse_up["dc"] = dc_up
+                    if self.debug:
+                        self.debug(up["name"], "dc", dc_up)
+                    return dx if fuse_up.get("need_dx", True) else None
                 self._ck(self.lib.avc_conv_block_tc(C.byref(d), self.tc_status.data_ptr(), st), f"conv_dgrad_tc_fold[{name}]")
                 if self.debug:
                     self.debug(name, "dx", dx)
@@ -684,22 +743,34 @@ class Engine:
         return out
 
     def _enc_bwd(self, P, G, enc, c, ctx, dout: A4):
-        for r1, r2, s, _blk_in in reversed(ctx["blocks"]):
-            dy1 = self.conv_bwd(P, G, r2, dout)
-            dout = self.conv_bwd(P, G, r1, dy1, dres=dout, dres_mode=L.RES_POOL if s > 1 else L.RES_SAME)
+        blocks = ctx["blocks"]
+        dc2 = None    # dc of the current block's second conv when the downstream data-gradient conv already produced it
+        for l in reversed(range(len(blocks))):
+            r1, r2, s, _blk_in = blocks[l]
+            f1 = dict(rec=r1, dcond=None, need_dx=False)           # r2's data gradient feeds r1's norm backward only
+            dy1 = self.conv_bwd(P, G, r2, dout, dc_pre=dc2, fuse_up=f1)
+            up = blocks[l - 1][1] if l > 0 else ctx["in"]           # whose output gradient r1's data gradient produces
+            f2 = dict(rec=up, dcond=None, need_dx=l > 0)            # ... needed again as the residual adjoint of block l-1
+            dout = self.conv_bwd(P, G, r1, dy1, dc_pre=f1["dc"], dres=dout, dres_mode=L.RES_POOL if s > 1 else L.RES_SAME, fuse_up=f2)
+            dc2 = f2["dc"]
         # in_conv: dgrad only towards the bank outputs (x needs no grad), ReLU mask fused
         cat, nb, cb = ctx["cat"], ctx["n_bank"], ctx["c_bank"]
         bank_out = cat.channels(0, nb * cb)
-        dbank = self.conv_bwd(P, G, ctx["in"], dout, mask=bank_out, dx_channels=nb * cb)
+        dbank = self.conv_bwd(P, G, ctx["in"], dout, dc_pre=dc2, mask=bank_out, dx_channels=nb * cb)
         x4 = ctx["x4"]
         st = self.stream
+        # bias gradients of the whole bank in one launch (the bank outputs all have x's length: K//2 + (K-1)//2 padding)
+        btab = self._bank_bias_table(enc, nb, G)
+        if btab is not None:
+            self._ck(self.lib.avc_bias_grad_groups(dbank.ptr, dbank.bstride, btab.data_ptr(), cb, x4.B, nb * cb, x4.T, st), "bias_grad_groups")
         for i in range(nb):
             name = f"{enc}.conv_bank.{i}"
             w = P[name + ".weight"]
             Cout, Cin, K = w.shape
             pl, pr, Tout = conv_geometry(K, 1, x4.T)
             dci = dbank.channels(i * cb, (i + 1) * cb)
-            self._ck(self.lib.avc_bias_grad(dci.ptr, dci.bstride, G[name + ".bias"].data_ptr(), x4.B, Cout, Tout, st), "bias_grad")
+            if btab is None:
+                self._ck(self.lib.avc_bias_grad(dci.ptr, dci.bstride, G[name + ".bias"].data_ptr(), x4.B, Cout, Tout, st), "bias_grad")
             wd = L.WgradDesc()
             wd.B, wd.Cin, wd.Cout, wd.K, wd.stride, wd.pad_left, wd.Tin, wd.Tout = x4.B, Cin, Cout, K, 1, pl, x4.T, Tout
             wd.x, wd.x_bstride, wd.dc, wd.dc_bstride = x4.ptr, x4.bstride, dci.ptr, dci.bstride
@@ -770,11 +841,20 @@ class Engine:
         nblk = c["n_conv_blocks"]
         dout = self.conv_bwd(P, G, ctx["out_rec"], ddec4)
         dconds = self.empty(*ctx["conds"].shape)
+        blocks = ctx["blocks"]
+        dc2 = None
         for l in reversed(range(nblk)):
-            r1, r2, up = ctx["blocks"][l]
-            dy1 = self.conv_bwd(P, G, r2, dout, dcond=dconds[:, 2 * l + 1])
-            dout = self.conv_bwd(P, G, r1, dy1, dres=dout, dres_mode=L.RES_UP if up > 1 else L.RES_SAME, dcond=dconds[:, 2 * l])
-        dz4 = self.conv_bwd(P, G, ctx["in_rec"], dout, need_dx=need_dz)
+            r1, r2, up = blocks[l]
+            f1 = dict(rec=r1, dcond=dconds[:, 2 * l], need_dx=False)
+            dy1 = self.conv_bwd(P, G, r2, dout, dcond=dconds[:, 2 * l + 1], dc_pre=dc2, fuse_up=f1)
+            if l > 0:
+                f2 = dict(rec=blocks[l - 1][1], dcond=dconds[:, 2 * l - 1], need_dx=True)
+            else:
+                f2 = dict(rec=ctx["in_rec"], dcond=None, need_dx=False)
+            dout = self.conv_bwd(P, G, r1, dy1, dc_pre=f1["dc"], dres=dout, dres_mode=L.RES_UP if up > 1 else L.RES_SAME,
+                                 dcond=dconds[:, 2 * l], fuse_up=f2)
+            dc2 = f2["dc"]
+        dz4 = self.conv_bwd(P, G, ctx["in_rec"], dout, dc_pre=dc2, need_dx=need_dz)
         demb = None
         aff = ctx["aff"]
         if isinstance(aff, dict):   # the 2n affine layers in three launches

@@ -59,6 +59,29 @@ class Inferencer(object):
         return self.model.inference(x, x_cond)
 
     @torch.no_grad()
+    def inference_ragged(self, xs, x_conds):
+        """Batched one-shot conversion of utterance pairs of DIFFERENT lengths (the serving form of the loop around
+        inference.py:62-70).  xs[i]: [T_i, n_mels], x_conds[i]: [Tc_i, n_mels] normalised mels on the device.
+        Pairs are bucketed by their exact (T_i, Tc_i): every bucket is one batched AE.inference call, so each
+        utterance gets bit-for-bit the result of converting it alone (InstanceNorm statistics are per sample and
+        no padded frame ever enters them -- no masking needed).  Returns the list of [8*ceil(T_i/8), n_mels] mels
+        in the input order (device tensors, normalised domain)."""
+        if len(xs) != len(x_conds):
+            raise ValueError("inference_ragged: xs and x_conds must have the same length")
+        buckets = {}
+        for i, (x, c) in enumerate(zip(xs, x_conds)):
+            buckets.setdefault((int(x.shape[0]), int(c.shape[0])), []).append(i)
+        out = [None] * len(xs)
+        for (_, _), idx in sorted(buckets.items()):
+            xb = torch.cat([self.utt_make_frames(xs[i]) for i in idx], dim=0)
+            cb = torch.cat([self.utt_make_frames(x_conds[i]) for i in idx], dim=0)
+            dec = self.model.inference(xb, cb)               # [n, n_mels, 8*ceil(T/8)]
+            for j, i in enumerate(idx):
+                out[i] = dec[j].transpose(0, 1)
+        self.model.engine(xs[0].device).check_tc_status()
+        return out
+
+    @torch.no_grad()
     def inference_one_utterance(self, x, x_cond):
         """x, x_cond: [T, n_mels] normalised mels on the device (inference.py:62-70)."""
         dec = self.model.inference(self.utt_make_frames(x), self.utt_make_frames(x_cond))

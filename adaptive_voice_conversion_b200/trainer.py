@@ -7,9 +7,10 @@ gradient buffer per iteration; the 1/world scale is folded into the clip/Adam ke
 the order backward -> all-reduce -> global-norm clip -> Adam matches a single-process
 step on the concatenated batch.
 
-With ``use_graph=True`` the step is captured once into CUDA graphs (static shapes) and
-replayed: graph A = zero-grad + forward + loss + backward, graph B = norm + Adam + weight
-re-pack; the all-reduce runs between them (N>1 only).
+``capture()`` records the step once into CUDA graphs (static shapes) and ``step()`` replays
+them: one graph for the whole step in a single process; with N > 1 graph A = zero-grad +
+forward + loss + backward, graph B = norm + Adam + weight re-pack, and the all-reduce runs
+between them.
 """
 from __future__ import annotations
 
@@ -110,8 +111,9 @@ class FusedTrainer:
             if eps is not None and eps.data_ptr() != self._static_eps.data_ptr():
                 self._static_eps.copy_(eps, non_blocking=True)
             self._graphs[0].replay()
-            self._allreduce()
-            self._graphs[1].replay()
+            if self._graphs[1] is not None:   # N > 1: the NCCL all-reduce sits between the two graphs
+                self._allreduce()
+                self._graphs[1].replay()
             return None
         n0 = L.launch_count()
         outs = self._fwd_bwd(x, eps)
@@ -134,8 +136,15 @@ class FusedTrainer:
         for _ in range(warmup):
             self.step(self._static, lam, eps=self._static_eps)
         torch.cuda.synchronize(self.dev)
-        ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        ga = torch.cuda.CUDAGraph()
         pool = torch.cuda.graph_pool_handle()
+        if self.world == 1:    # one process: the whole step (zero-grad .. weight re-pack) is ONE graph
+            with torch.cuda.graph(ga, pool=pool):
+                self._fwd_bwd(self._static, self._static_eps)
+                self._update()
+            self._graphs = (ga, None)
+            return self._static
+        gb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(ga, pool=pool):
             self._fwd_bwd(self._static, self._static_eps)
         with torch.cuda.graph(gb, pool=pool):

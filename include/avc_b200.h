@@ -54,6 +54,12 @@ extern "C" {
  * its residual branch (res / res_mode / res_T read as in avc_fold_desc): Tout = T+pl+pr columns are
  * computed, `out` receives the T folded time steps (what avc_fold_add_fwd produces in a second pass). */
 #define AVC_F_FOLD 4
+/* with AVC_F_FOLD on the persistent kernel: the epilogue also runs the backward of the UPSTREAM block's InstanceNorm /
+ * AdaIN / ReLU on the folded gradient (what avc_norm_bwd does in a second pass).  The descriptor's norm, relu, eps, cond,
+ * save_c, stats (inputs) and dc, dcond, dbias (outputs) then describe that upstream block -- same [B][Cout][T] shape as
+ * this conv's folded output, no pixel shuffle, Cout <= 128 -- and `out` may be null when nobody else needs the folded
+ * gradient itself.  dc is rounded to TF32 when AVC_F_ROUND_OUT is set. */
+#define AVC_F_NORMBWD 8
 #define AVC_FOLD_FLAGS(pl, pr) (AVC_F_FOLD | ((pl) << 8) | ((pr) << 16))
 
 #define AVC_PACK_FWD 0   /* P[ci][j][co]  = W[co][ci][j]                                   */
@@ -136,6 +142,7 @@ void avc_tc2_set_variant(int v);
  *   "tc_uniform_issue"  (AVC_TC_ISSUE=uniform|legacy)   tcgen05 issue loops on the uniform datapath
  *   "wgrad_reduce_v2"   (AVC_WGRAD_REDUCE=v2|v1)        unrolled partial-sum reduction of conv_wgrad_tc
  *   "tc_conv_v2"        (AVC_TC_CONV=v2|v1)             persistent, epilogue-overlapped conv block kernel (default on)
+ *   "wgrad_split"       (AVC_WGRAD_KERNEL=split|r1)     weight gradient with a dedicated MMA warp (default off until it wins)
  * avc_set_option returns AVC_ERR_INVALID for an unknown name; avc_get_option returns -1. */
 int avc_set_option(const char* name, int value);
 int avc_get_option(const char* name);
@@ -217,6 +224,10 @@ int avc_unpack_a4(const float* a4, int64_t a4_bstride, float* planar, int B, int
 
 /* sum over (b, t) of an A4 tensor -> out[C] (+=): bias gradient of a conv without epilogue. */
 int avc_bias_grad(const float* dc, int64_t bstride, float* dbias, int B, int C, int T, void* stream);
+/* The same for a tensor whose C channels are `C / group_c` layers side by side (the conv-bank gradient): channel c adds
+ * into dbias_tab_dev[c / group_c][c % group_c]; dbias_tab_dev is a DEVICE array of C / group_c pointers.  One launch
+ * instead of one per layer. */
+int avc_bias_grad_groups(const float* dc, int64_t bstride, float* const* dbias_tab_dev, int group_c, int B, int C, int T, void* stream);
 
 /* AdaptiveAvgPool1d(1) (model.py:231,273) and its adjoint. */
 int avc_time_mean_fwd(const float* a4, int64_t bstride, float* out /*[B][C]*/, int B, int C, int T, void* stream);
@@ -329,6 +340,9 @@ int avc_tc_probe_gemm(const float* a_img, int a_bytes, const float* b_img, int b
 /* Read-back variant of the self-test: the accumulator is read with 16-column tcgen05.ld's starting at
  * column `shift` + 16 j (any shift >= 0; columns below `shift` are left untouched in D). */
 void avc_tc_probe_set_ld_shift(int shift);
+/* Store-path probe (diagnostic): `ctas` CTAs of 256 threads each write bytes_per_cta (multiple of 4096) to their own
+ * region of dst; mode 0 = STG.128, 1 = 2 KB bulk (TMA) stores from shared memory, 2 = half each; cycles[cta] = span. */
+int avc_probe_store(float* dst, long long bytes_per_cta, int ctas, int mode, long long* cycles, void* stream);
 
 const char* avc_last_error(void);
 /* "sm_100a" build tag, number of kernels launched so far by this process (for bench.py's

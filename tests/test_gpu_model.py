@@ -242,7 +242,7 @@ def test_graph_step_matches_eager(tmp_path):
         lt, gt = (1e-5, 1e-4) if i == 0 else (2e-3, 3e-1)
         assert abs(l0 - l1) / l0 < lt and abs(k0 - k1) / k0 < lt and abs(n0 - n1) / n0 < gt, (i, l0, l1, k0, k1, n0, n1)
         assert rel_l2(g1, g0) < gt, (i, rel_l2(g1, g0))
-        assert rel_l2(p1, p0) < 1e-3
+        assert rel_l2(p1, p0) < (1e-3 if i == 0 else 5e-3), (i, rel_l2(p1, p0))
 
 
 def test_resume_restores_the_annealing_position(tmp_path):
@@ -269,6 +269,30 @@ def test_resume_restores_the_annealing_position(tmp_path):
     for k, v in s1.model.state_dict().items():      # same weights were loaded before the two extra steps
         assert v.shape == s2.model.state_dict()[k].shape
     assert float(s2.opt.step_dev.item()) == 5.0     # Adam's step counter resumed too (3 loaded + 2)
+
+
+def test_inference_ragged_batch_equals_per_utterance(precision):
+    """Inferencer.inference_ragged: (src, tgt) pairs of different lengths, bucketed by exact length, each utterance
+    identical to converting it alone and within tolerance of the reference (inference.py:62-65, model.py:387-391)."""
+    from adaptive_voice_conversion_b200.inference import Inferencer
+    cfg = orc.default_config(80)
+    args = types.SimpleNamespace(attr=None, model=None, source=None, target=None, output=None, sample_rate=24000)
+    inf = Inferencer(cfg, args)
+    inf.model.load_state_dict(orc.init_state(cfg, seed=0), strict=True)
+    lens = [(301, 173), (128, 96), (301, 173), (64, 301), (128, 96), (301, 173), (77, 50)]
+    xs = [torch.randn((t, 80), generator=torch.Generator().manual_seed(10 + i)).cuda() for i, (t, _) in enumerate(lens)]
+    cs = [torch.randn((tc, 80), generator=torch.Generator().manual_seed(40 + i)).cuda() for i, (_, tc) in enumerate(lens)]
+    outs = inf.inference_ragged(xs, cs)
+    assert [o.shape[0] for o in outs] == [8 * ((t + 7) // 8) for t, _ in lens]
+    for i, (x, c) in enumerate(zip(xs, cs)):
+        _, mel = inf.inference_one_utterance(x, c)
+        # same kernels, per-sample arithmetic (bit-identical wherever the tile plan does not depend on the batch;
+        # a different InstanceNorm summation order is amplified to the TF32 noise floor, tests/test_gpu_properties.py)
+        assert relerr(outs[i].cpu(), torch.from_numpy(mel)) < tol(precision, 1e-5, 2e-3), i
+        if i in (0, 3, 6):
+            with torch.no_grad():
+                ref = orc.ae_inference(orc.init_state(cfg, 0), cfg, x.cpu().t()[None], c.cpu().t()[None])
+            assert relerr(outs[i].t()[None], ref) < tol(precision, REL, 8e-3), i
 
 
 def test_inferencer_api(tmp_path, precision):

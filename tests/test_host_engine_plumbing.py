@@ -78,7 +78,7 @@ def test_pointer_tables_are_complete_before_a_step(rig):
     e, P, G = rig
     e.prepare_tables(P, G)
     before = {k: id(v[1]) for k, v in e._ptr_tables.items()}
-    assert len(before) == 4
+    assert len(before) == 6      # params + grads of the dense stack and of the affine layers, bank bias gradients of both encoders
     full_step(e, P, G)
     assert {k: id(v[1]) for k, v in e._ptr_tables.items()} == before      # nothing was (re)built mid-step
     # a moved parameter invalidates its table
