@@ -54,6 +54,7 @@ struct Tc2Args {
   uint32_t stage_bytes, w_bytes, x_chunk_bytes;
   uint32_t off_tile, off_par, off_stat;  // byte offsets inside dynamic shared memory
   int patch;    // 1: the patch warps sit between the bulk copy and the MMAs (halo rows and/or TF32 rounding)
+  int npatch;   // patch threads that take part (32: one warp is enough for a few reflect rows; 128 otherwise)
   int variant;  // bit 0: `c` rows leave through bulk (TMA) stores; bit 1: `out` rows too (written back in place)
   int* status;
   long long* dbg;
@@ -113,7 +114,10 @@ __device__ __forceinline__ TileCoord t2_decode(const Tc2Args& a, int tile) {
 // rows / samples outside the tensor arrive as zeros (that IS the zero padding of the data-gradient convs).
 __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a, const __grid_constant__ CUtensorMap tmx) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar_full[T2_MAX_STAGES], bar_ready[T2_MAX_STAGES], bar_empty[T2_MAX_STAGES], bar_accf[2], bar_acce[2];
+  // per stage: full = weights landed, fullx = input rows landed (they are small and issued first, so the patch step
+  // runs while the 5x larger weight copy is still in flight), ready = patched, empty = consumed by the MMAs
+  __shared__ uint64_t bar_full[T2_MAX_STAGES], bar_fullx[T2_MAX_STAGES], bar_ready[T2_MAX_STAGES], bar_empty[T2_MAX_STAGES], bar_accf[2],
+      bar_acce[2];
   __shared__ uint32_t tmem_slot;
   const avc_conv_desc& d = a.d;
   const int tid = threadIdx.x, warp = tc::warp_idx_sync(), lane = tid & 31;
@@ -122,7 +126,8 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
   if (tid == 0) {
     for (int s = 0; s < a.nstage; ++s) {
       tc::mbar_init(&bar_full[s], 1);
-      tc::mbar_init(&bar_ready[s], 128);
+      tc::mbar_init(&bar_fullx[s], 1);
+      tc::mbar_init(&bar_ready[s], (uint32_t)a.npatch);
       tc::mbar_init(&bar_empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -150,6 +155,16 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
       const TileCoord c = t2_decode(a, tile);
       const float* wsrc = d.w_tc + (size_t)c.mtile * a.nslab * (a.w_bytes / 4);
       const int tstart = c.t0 * S - d.pad_left;   // first input position of the staged rows (may be negative)
+      // warm L2 with the NEXT tile's input rows (they usually come from HBM: a saved activation, or an input the L2
+      // no longer holds), so that the latency-sensitive stage copies of that tile hit L2 like the weights do
+      if (tile + (int)gridDim.x < a.ntiles && (a.variant & 8)) {   // opt-in: measured slower (the prefetches occupy the copy engine), AVC_T2_VARIANT bit 3
+        const TileCoord cn = t2_decode(a, tile + gridDim.x);
+        if (cn.b0 != c.b0 || cn.t0 != c.t0) {   // (another m-tile of the same samples reads the same rows)
+          const int tsn = cn.t0 * S - d.pad_left;
+          for (int i = lane; i < a.nslab; i += 32) tc::tensor_prefetch_l2_4d(&tmx, 0, tsn, cn.b0, i * 4);
+        }
+      }
+      __syncwarp();
       for (int i = 0; i < a.nslab; ++i) {
         const long long w0 = a.dbg ? clock64() : 0;
         if (!first_round) ok = __all_sync(0xffffffffu, tc::mbar_wait(&bar_empty[s], ph ^ 1u, a.status, 2));
@@ -157,9 +172,10 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
         if (!ok) break;
         uint8_t* sw = smem + (size_t)s * a.stage_bytes;
         if (tc::elect_one()) {
-          tc::mbar_arrive_expect_tx(&bar_full[s], a.w_bytes + 4u * a.x_chunk_bytes);
+          tc::mbar_arrive_expect_tx(&bar_fullx[s], 4u * a.x_chunk_bytes);
+          tc::tensor_g2s_4d(sw + a.w_bytes, &tmx, 0, tstart, c.b0, i * 4, &bar_fullx[s]);
+          tc::mbar_arrive_expect_tx(&bar_full[s], a.w_bytes);
           tc::bulk_g2s(sw, wsrc + (size_t)i * (a.w_bytes / 4), a.w_bytes, &bar_full[s]);
-          tc::tensor_g2s_4d(sw + a.w_bytes, &tmx, 0, tstart, c.b0, i * 4, &bar_full[s]);
         }
         __syncwarp();
         if (++s == a.nstage) { s = 0; ph ^= 1u; first_round = false; }
@@ -190,7 +206,8 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
       const uint32_t dcol = tb + buf * 256u;
       for (int i = 0; i < a.nslab; ++i) {
         const long long w0 = a.dbg ? clock64() : 0;
-        ok = __all_sync(0xffffffffu, tc::mbar_wait(a.patch ? &bar_ready[s] : &bar_full[s], ph, a.status, 3));
+        ok = __all_sync(0xffffffffu, tc::mbar_wait(a.patch ? &bar_ready[s] : &bar_fullx[s], ph, a.status, 3) &&
+                                         tc::mbar_wait(&bar_full[s], ph, a.status, 3));
         const long long w1 = a.dbg ? clock64() : 0;
         dbg0 += w1 - w0;
         if (!ok) break;
@@ -246,45 +263,71 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
     uint32_t ph = 0;
     bool ok = true;
     long long dbg0 = 0, dbg1 = 0;
-    for (int tile = blockIdx.x; a.patch && tile < a.ntiles && ok; tile += gridDim.x) {
+    for (int tile = blockIdx.x; a.patch && ptid < a.npatch && tile < a.ntiles && ok; tile += gridDim.x) {
       const TileCoord c = t2_decode(a, tile);
       const int pbeg = c.t0 * S - d.pad_left;
       const int nr = (c.tw - 1) * S + K;  // rows one sample needs
       const int p_lo = max(0, pbeg), p_hi = min(d.Tin, pbeg + a.R);   // input positions present in the staged rows
       const int ncopy = max(0, min(p_hi, pbeg + nr) - p_lo), r_lo = p_lo - pbeg;
       const int nh = refl ? nr - ncopy : 0;
+      // The halo assignment of a thread is the same for every slab of the tile: resolve it ONCE (the index arithmetic
+      // -- two runtime divisions and the mirror position -- was a ~600-cycle dependent chain in front of every stage).
+      // Thread e handles (sample g, halo row h, plane q); more than 128 entries fall back to the generic loop.
+      const int nent = c.nsamp * nh * 4;
+      int h_dst = -1, h_src = -1, h_glob = -1;   // float4 offsets inside the stage's x region; global source position
+      if (ptid < nent) {   // (nent <= npatch entries are resolved here, the rest in the generic loop below)
+        const int q = ptid & 3, r = ptid >> 2;
+        const int g = r / nh, h = r - g * nh;
+        const int u = h < r_lo ? h : h + ncopy;
+        const int p = src_pos(pbeg + u, d.Tin, AVC_PAD_REFLECT, 1);
+        h_dst = q * a.srows + g * a.R + u;
+        if (p >= p_lo && p < p_hi) h_src = q * a.srows + g * a.R + (p - pbeg);
+        else if (p >= 0) h_glob = p;
+      }
+      const int hq = ptid & 3, hg = (ptid >> 2) / (nh > 0 ? nh : 1);
       for (int i = 0; i < a.nslab && ok; ++i) {
         const long long w0 = a.dbg ? clock64() : 0;
-        ok = tc::mbar_wait(&bar_full[s], ph, a.status, 4);
+        ok = tc::mbar_wait(&bar_fullx[s], ph, a.status, 4);
         const long long w1 = a.dbg ? clock64() : 0;
         dbg0 += w1 - w0;
         if (!ok) break;
         float4* sx = reinterpret_cast<float4*>(smem + (size_t)s * a.stage_bytes + a.w_bytes);
         bool wrote = false;
         if (rnd) {
-          for (int e = ptid; e < c.nsamp * ncopy * 4; e += 128) {
-            const int q = e & 3, r = e >> 2;
-            const int g = r / ncopy, t = r - g * ncopy;
-            float4* p = sx + (size_t)q * a.srows + g * a.R + r_lo + t;
+          // every row of every plane (halo / gap rows included: rounding them again is harmless): no index arithmetic
+          const int nrow = c.nsamp * a.R;
+          for (int e = ptid; e < nrow * 4; e += 128) {   // (rounding always runs with all 128 patch threads)
+            float4* p = sx + (size_t)(e & 3) * a.srows + (e >> 2);
             *p = t2_round4(*p);
-            wrote = true;
           }
+          wrote = true;
+          if (nh > 0) t2_bar_sync(1, 128);   // the reflect rows below copy ROUNDED rows
         }
-        // halo rows: one (sample, row, 4-channel plane) per thread.  A source row may be rounded in place by
-        // another thread at the same time: rounding is idempotent, either version gives the same result.
-        for (int e = ptid; e < c.nsamp * nh * 4; e += 128) {
+        if (h_dst >= 0) {
+          float4 v = zero4();
+          if (h_src >= 0) v = sx[h_src];
+          else if (h_glob >= 0) {
+            v = ldg4(d.in + (size_t)(c.b0 + hg) * d.in_bstride + ((size_t)(i * 4 + hq) * d.Tin + h_glob) * 4);
+            if (rnd) v = t2_round4(v);
+          }
+          sx[h_dst] = v;
+          wrote = true;
+        }
+        for (int e = ptid + a.npatch; e < nent; e += a.npatch) {   // more halo entries than patch threads (large K x G): generic path
           const int q = e & 3, r = e >> 2;
           const int g = r / nh, h = r - g * nh;
-          const int u = h < r_lo ? h : h + ncopy;  // row inside the sample's segment
+          const int u = h < r_lo ? h : h + ncopy;
           const int p = src_pos(pbeg + u, d.Tin, AVC_PAD_REFLECT, 1);
           float4 v = zero4();
           if (p >= p_lo && p < p_hi) v = sx[(size_t)q * a.srows + g * a.R + (p - pbeg)];
-          else if (p >= 0) v = ldg4(d.in + (size_t)(c.b0 + g) * d.in_bstride + ((size_t)(i * 4 + q) * d.Tin + p) * 4);
-          if (rnd) v = t2_round4(v);
+          else if (p >= 0) {
+            v = ldg4(d.in + (size_t)(c.b0 + g) * d.in_bstride + ((size_t)(i * 4 + q) * d.Tin + p) * 4);
+            if (rnd) v = t2_round4(v);
+          }
           sx[(size_t)q * a.srows + g * a.R + u] = v;
           wrote = true;
         }
-        if (wrote && !(a.variant & 4)) tc::fence_proxy_async_smem();   // only writers pay for the proxy fence (bit 2: timing experiment, WRONG results)
+        if (wrote) tc::fence_proxy_async_smem();   // only writers pay for the proxy fence
         tc::mbar_arrive(&bar_ready[s]);
         if (a.dbg) dbg1 += clock64() - w1;
         if (++s == a.nstage) { s = 0; ph ^= 1u; }
@@ -812,6 +855,8 @@ int conv_block_tc2_launch(const avc_conv_desc* d, int* status, void* stream) {
   a.status = status;
   a.dbg = g_tc2_dbg;
   a.patch = (!(d->flags & AVC_F_IN_TF32) || (d->pad_mode == AVC_PAD_REFLECT && d->K > 1)) ? 1 : 0;
+  // a few reflect rows of a pre-rounded input: one warp does it (three fewer warps polling the stage barriers)
+  a.npatch = ((d->flags & AVC_F_IN_TF32) && a.G * (d->K - 1) * 4 <= 32) ? 32 : 128;
   a.variant = t2_variant();
   CUtensorMap tmx;
   {

@@ -381,7 +381,7 @@ static Option g_opts[] = {
     {"tc_uniform_issue", "AVC_TC_ISSUE", "uniform", "legacy", AVC_DEFAULT_TC_UNIFORM_ISSUE, -1},
     {"wgrad_reduce_v2", "AVC_WGRAD_REDUCE", "v2", "v1", AVC_DEFAULT_WGRAD_REDUCE_V2, -1},
     {"tc_conv_v2", "AVC_TC_CONV", "v2", "v1", 1, -1},   // persistent conv block kernel (conv_tc2.cu); v1 = conv_tc.cu
-    {"wgrad_split", "AVC_WGRAD_KERNEL", "split", "r1", 0, -1},   // weight gradient with a dedicated MMA warp (conv_wgrad_split_kernel)
+    {"wgrad_split", "AVC_WGRAD_KERNEL", "split", "r1", 1, -1},   // weight gradient with a dedicated MMA warp (conv_wgrad_split_kernel)
 };
 static int opt_value(int i) {
   Option& o = g_opts[i];

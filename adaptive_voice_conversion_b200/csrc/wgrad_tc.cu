@@ -305,26 +305,43 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_wgrad_split_kernel(const W
       uint8_t* sX = sA + a.x_off;
       const int b0 = tile * a.G;
       const int nsamp = min(a.G, d.B - b0);
-      for (int r = tid; r < nsamp * T; r += WS_STAGE_THREADS) {
-        const int g = r / T, t = r - g * T;
-        const float* src = d.dc + (size_t)(b0 + g) * d.dc_bstride + (size_t)t * 4;
-#pragma unroll 8
-        for (int q = 0; q < 32; ++q) {
-          const int co = co0 + 4 * q;
-          const bool cv = co < d.Cout;
-          cp_async16(sA + mn_unit_off(q, r, atomA), src + (size_t)((cv ? co : 0) >> 2) * T * 4, cv);
+      // Unit -> lane mapping: a warp writes 4 rows x the 8 units of one 128-byte atom row = four whole bank sweeps.
+      // (One row per lane, as in the round-1 kernel, puts 32 lanes on 4 bank groups: an 8-way conflict that made the
+      // shared-memory side of every cp.async 8x slower -- staging was 6.5 K cycles per tile against 1.5 K of issue.)
+      // Each thread walks rows r_lo, r_lo + 16 (dc: + 8), ... with (g, t) kept incrementally: no division per unit.
+      // Unit -> lane mapping: a warp writes 4 rows x the 8 units of one 128-byte atom row = four whole bank sweeps, and
+      // each thread walks rows r_lo, r_lo + 8 (x: + 16), ... with (g, t) kept incrementally: no division per unit.
+      // (Measured alternatives, tools/diag_wgrad.py: one row per lane as in round 1 -- same time; LDG.128 -> registers
+      // -> STS.128 with eight loads in flight -- 40 % slower.  The ~6.5 K cycles per 97 KB tile are not the bank mapping.)
+      {
+        // dc: 4 atoms x 8 units per row; 256 threads = 8 warps = (2 row groups of 4 rows) x 4 atoms
+        const int q = ((tid >> 5) & 3) * 8 + (tid & 7), r_lo = ((tid >> 7) << 2) + ((tid >> 3) & 3);
+        const int co = co0 + 4 * q;
+        const bool cv = co < d.Cout;
+        const float* colsrc = d.dc + (size_t)((cv ? co : 0) >> 2) * T * 4;
+        int g = r_lo / T, t = r_lo - g * T;
+        for (int r = r_lo; r < nsamp * T; r += 8) {
+          cp_async16(sA + mn_unit_off(q, r, atomA), colsrc + (size_t)(b0 + g) * d.dc_bstride + (size_t)t * 4, cv);
+          t += 8;
+          while (t >= T) { t -= T; ++g; }
         }
       }
-      for (int r0 = tid; r0 < nsamp * TX; r0 += WS_STAGE_THREADS) {
-        const int g = r0 / TX, u = r0 - g * TX;
-        const int r = S == 1 ? r0 : g * 2 * H + (u & 1) * H + (u >> 1);
-        const int p = src_pos(u - d.pad_left, d.Tin, AVC_PAD_REFLECT, 1);
-        const float* src = d.x + (size_t)(b0 + g) * d.x_bstride + (size_t)(p >= 0 ? p : 0) * 4;
-#pragma unroll 8
-        for (int q = 0; q < nq_x; ++q) {
-          const int ci = ci0 + 4 * q;
-          const bool v = ci < d.Cin && p >= 0;
-          cp_async16(sX + mn_unit_off(q, r, atomX), src + (size_t)((v ? ci : 0) >> 2) * d.Tin * 4, v);
+      {
+        // x: ntpad/32 atoms x 8 units per row; a warp = 4 rows of one atom, the 8 warps cover natom atoms x (8/natom) row groups
+        const int natom = nq_x >> 3, wpa = 8 / natom;             // warps per atom
+        const int w = tid >> 5, atom = w % natom, rg = w / natom;  // row group of this warp
+        const int q = atom * 8 + (tid & 7), r_lo = (rg << 2) + ((tid >> 3) & 3), rstep = wpa << 2;
+        const int ci = ci0 + 4 * q;
+        const bool civ = ci < d.Cin;
+        const float* colsrc = d.x + (size_t)((civ ? ci : 0) >> 2) * d.Tin * 4;
+        int g = r_lo / TX, u = r_lo - g * TX;
+        for (int r0 = r_lo; r0 < nsamp * TX; r0 += rstep) {
+          const int r = S == 1 ? r0 : g * 2 * H + (u & 1) * H + (u >> 1);
+          const int p = src_pos(u - d.pad_left, d.Tin, AVC_PAD_REFLECT, 1);
+          const bool v = civ && p >= 0;
+          cp_async16(sX + mn_unit_off(q, r, atomX), colsrc + (size_t)(b0 + g) * d.x_bstride + (size_t)(p >= 0 ? p : 0) * 4, v);
+          u += rstep;
+          while (u >= TX) { u -= TX; ++g; }
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
@@ -338,8 +355,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_wgrad_split_kernel(const W
       }
     }
   } else {
-    // ============================================================ MMA issuer (warp 8), uniform datapath
-    const uint32_t idesc = tc::make_idesc_tf32(128, a.ntpad, 1, 1);
+    // ============================================================ MMA issuer (warp 8), uniform datapath.
+    // ALL TAPS IN ONE MMA: for a 32-channel block of x, tap j is the same swizzled atom one row (128 B) further, so
+    // a B descriptor with LBO = 128 B addresses the K taps as K consecutive 32-column atoms: one MMA of N = 32 K
+    // columns per k-step and channel block (stride 2: the even and the odd taps form two such groups) instead of K
+    // MMAs of N = 64 -- the dc operand is read once per k-step instead of K times (the MMAs here are bound by
+    // shared-memory operand traffic), 2 instead of 5 instructions per k-step.
+    const int NT = K * 32;                 // TMEM columns of one 32-channel block
+    const int natom = a.ntpad >> 5;
+    const int ne = (K + 1) >> 1, no = K >> 1;
+    const uint32_t idesc_all = tc::make_idesc_tf32(128, NT, 1, 1);
+    const uint32_t idesc_e = tc::make_idesc_tf32(128, 32 * ne, 1, 1), idesc_o = tc::make_idesc_tf32(128, no ? 32 * no : 32, 1, 1);
     const uint32_t tb_u = __shfl_sync(0xffffffffu, tbase, 0);
     const uint32_t smem_base = __shfl_sync(0xffffffffu, tc::smem_u32(smem), 0);
     const uint32_t hi = tc::sdesc_hi(512, 1);
@@ -352,37 +378,23 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_wgrad_split_kernel(const W
       tc::tc_fence_after();
       const long long q2 = a.dbg ? clock64() : 0;
       const uint32_t sbase = smem_base + (uint32_t)(it_u & 1) * a.buf_bytes;
-      const uint32_t a_lo0 = tc::sdesc_lo(sbase, atomA), b_lo0 = tc::sdesc_lo(sbase + a.x_off, atomX);
+      const uint32_t a_lo0 = tc::sdesc_lo(sbase, atomA);
       for (int g = 0; g < nsamp_u; ++g) {
         uint64_t a_desc = tc::sdesc64(a_lo0 + (uint32_t)(g * T) * 8u, hi);
-        uint64_t b_ks = tc::sdesc64(b_lo0 + (uint32_t)(S == 1 ? g * TX : g * 2 * H) * 8u, hi);
+        const uint32_t xrow0 = (uint32_t)(S == 1 ? g * TX : g * 2 * H) * 8u;   // in 16-byte descriptor units
         for (int ks = 0; ks < nks; ++ks) {
           const uint32_t acc = (it_u | g | ks) ? 1u : 0u;
-          uint32_t dcol = tb_u;
-          if (S == 1) {
-            uint64_t b_desc = b_ks;
-            if (K == 5) {
-#pragma unroll
-              for (int j = 0; j < 5; ++j) {
-                tc::mma_tf32_elect(dcol, a_desc, b_desc, idesc, acc);
-                b_desc += 8u;
-                dcol += (uint32_t)a.ntpad;
-              }
+          for (int cb = 0; cb < natom; ++cb) {
+            const uint32_t b_lo = tc::sdesc_lo(sbase + a.x_off + (uint32_t)cb * atomX, 128u) + xrow0 + (uint32_t)ks * 64u;
+            const uint32_t dcol = tb_u + (uint32_t)(cb * NT);
+            if (S == 1) {
+              tc::mma_tf32_elect(dcol, a_desc, tc::sdesc64(b_lo, hi), idesc_all, acc);
             } else {
-              for (int j = 0; j < K; ++j) {
-                tc::mma_tf32_elect(dcol, a_desc, b_desc, idesc, acc);
-                b_desc += 8u;
-                dcol += (uint32_t)a.ntpad;
-              }
-            }
-          } else {
-            for (int j = 0; j < K; ++j) {
-              tc::mma_tf32_elect(dcol, a_desc, b_ks + (uint32_t)((j & 1) * H + (j >> 1)) * 8u, idesc, acc);
-              dcol += (uint32_t)a.ntpad;
+              tc::mma_tf32_elect(dcol, a_desc, tc::sdesc64(b_lo, hi), idesc_e, acc);
+              if (no) tc::mma_tf32_elect(dcol + (uint32_t)(32 * ne), a_desc, tc::sdesc64(b_lo + (uint32_t)H * 8u, hi), idesc_o, acc);
             }
           }
           a_desc += 64u;
-          b_ks += 64u;
         }
       }
       __syncwarp();
@@ -399,16 +411,20 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_wgrad_split_kernel(const W
   tc::tc_fence_after();
   if (a.dbg) q4 = clock64();
   if (ok && tile1 > tile0 && warp < 8) {
+    // TMEM column of (32-channel block cb, tap j, channel c) = cb * 32 K + slot(j) * 32 + c, slot(j) = j (stride 1) or the
+    // even taps first (stride 2); 8 warps: lane quarter = warp & 3, the 16-column chunks are split between its two warps
     const int quarter = warp & 3, half = warp >> 2;
     const int co = co0 + quarter * 32 + lane;
     const uint32_t lane_addr = tbase + ((uint32_t)(quarter * 32) << 16);
     const int nch = a.ntpad >> 4;
+    const int NT = K * 32, ne = (K + 1) >> 1;
     for (int j = 0; j < K; ++j) {
+      const int slot = S == 1 ? j : ((j & 1) ? ne + (j >> 1) : (j >> 1));
       float* sbase = a.scratch + (((size_t)(ATOMIC ? 0 : sl) * K + j) * (size_t)(d.Cin >> 2)) * (size_t)a.coutp * 4;
       for (int ch = half; ch < nch; ch += 2) {
         const int c0 = ch << 4;
         float v[16];
-        tc::tmem_ld16(lane_addr + (uint32_t)(j * a.ntpad + c0), v);
+        tc::tmem_ld16(lane_addr + (uint32_t)((c0 >> 5) * NT + slot * 32 + (c0 & 31)), v);
 #pragma unroll
         for (int i4 = 0; i4 < 16; i4 += 4) {
           const int ci = ci0 + c0 + i4;

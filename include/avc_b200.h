@@ -142,7 +142,7 @@ void avc_tc2_set_variant(int v);
  *   "tc_uniform_issue"  (AVC_TC_ISSUE=uniform|legacy)   tcgen05 issue loops on the uniform datapath
  *   "wgrad_reduce_v2"   (AVC_WGRAD_REDUCE=v2|v1)        unrolled partial-sum reduction of conv_wgrad_tc
  *   "tc_conv_v2"        (AVC_TC_CONV=v2|v1)             persistent, epilogue-overlapped conv block kernel (default on)
- *   "wgrad_split"       (AVC_WGRAD_KERNEL=split|r1)     weight gradient with a dedicated MMA warp (default off until it wins)
+ *   "wgrad_split"       (AVC_WGRAD_KERNEL=split|r1)     weight gradient with a dedicated MMA warp, all taps in one MMA (default on)
  * avc_set_option returns AVC_ERR_INVALID for an unknown name; avc_get_option returns -1. */
 int avc_set_option(const char* name, int value);
 int avc_get_option(const char* name);
