@@ -56,6 +56,8 @@ struct Tc2Args {
   int patch;    // 1: the patch warps sit between the bulk copy and the MMAs (halo rows and/or TF32 rounding)
   int npatch;   // patch threads that take part (32: one warp is enough for a few reflect rows; 128 otherwise)
   int variant;  // bit 0: `c` rows leave through bulk (TMA) stores; bit 1: `out` rows too (written back in place)
+                // ABLATION bits (timing probes only, results are WRONG; tools/diag_ablate.py): 16 weight copies shrunk to
+                // 1 KB, 32 no store pass, 64 no MMAs, 128 no TMEM pass, 256 no input-row copies
   int* status;
   long long* dbg;
 };
@@ -172,10 +174,14 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
         if (!ok) break;
         uint8_t* sw = smem + (size_t)s * a.stage_bytes;
         if (tc::elect_one()) {
-          tc::mbar_arrive_expect_tx(&bar_fullx[s], 4u * a.x_chunk_bytes);
-          tc::tensor_g2s_4d(sw + a.w_bytes, &tmx, 0, tstart, c.b0, i * 4, &bar_fullx[s]);
-          tc::mbar_arrive_expect_tx(&bar_full[s], a.w_bytes);
-          tc::bulk_g2s(sw, wsrc + (size_t)i * (a.w_bytes / 4), a.w_bytes, &bar_full[s]);
+          if (a.variant & 256) tc::mbar_arrive(&bar_fullx[s]);
+          else {
+            tc::mbar_arrive_expect_tx(&bar_fullx[s], 4u * a.x_chunk_bytes);
+            tc::tensor_g2s_4d(sw + a.w_bytes, &tmx, 0, tstart, c.b0, i * 4, &bar_fullx[s]);
+          }
+          const uint32_t wb = (a.variant & 16) ? 1024u : a.w_bytes;
+          tc::mbar_arrive_expect_tx(&bar_full[s], wb);
+          tc::bulk_g2s(sw, wsrc + (size_t)i * (a.w_bytes / 4), wb, &bar_full[s]);
         }
         __syncwarp();
         if (++s == a.nstage) { s = 0; ph ^= 1u; first_round = false; }
@@ -216,6 +222,7 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
         const uint32_t a_lo0 = tc::sdesc_lo(sw, 2048), b_lo0 = tc::sdesc_lo(sw + a.w_bytes, a.x_chunk_bytes);
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
+          if (a.variant & 64) break;
           uint64_t a_desc = tc::sdesc64(a_lo0 + (uint32_t)ks * (4096 >> 4), d_hi);
           uint64_t b_desc = tc::sdesc64(b_lo0 + (uint32_t)ks * ks_b, d_hi);
           if (K == 5) {
@@ -379,7 +386,7 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
       const int nch = (ncol + 15) >> 4;
       const uint32_t lane_addr = tbase + ((uint32_t)(quarter * 32) << 16) + buf * 256u;
       // ---------------- pass 0: TMEM -> (+bias, InstanceNorm sums) -> staged A4 tile
-      if (ok) {
+      if (ok && !(a.variant & 128)) {
         float* srow = stile + ((size_t)(col_l >> 2) * P) * 4 + (col_l & 3);
         for (int g = 0; g < c.nsamp; ++g) {
           float s1 = 0.f, s2 = 0.f;
@@ -420,7 +427,7 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
           if (fwd_norm) stat[(half * a.G + g) * 128 + col_l] = make_float2(s1, s2);
         }
       }
-      if (a.variant) tc::fence_proxy_async_smem();   // the staged rows will be read by bulk (async-proxy) stores
+      if (a.variant & 3) tc::fence_proxy_async_smem();   // the staged rows will be read by bulk (async-proxy) stores
       tc::tc_fence_before();
       tc::mbar_arrive(&bar_acce[buf]);  // the accumulator is free: the MMA warp may start tile tl+2 into it
       const long long e2 = a.dbg ? clock64() : 0;
@@ -458,7 +465,7 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
       t2_bar_sync(2, 256);
       const long long e3 = a.dbg ? clock64() : 0;
       // ---------------- pass B: staged tile -> c / out, thread = one 16-byte A4 unit, lanes along time
-      if (ok) {
+      if (ok && !(a.variant & 32)) {
         const int nq = min(32, (d.Cout - c.mtile * 128) >> 2);  // valid 4-row chunks of this tile
         const float4* st4p = reinterpret_cast<const float4*>(stile);
         const float4* par4 = reinterpret_cast<const float4*>(par);
@@ -581,7 +588,7 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
               }
             }
           }
-        } else if (!shuf && !d.mask && ots == 1 && a.variant == 0) {
+        } else if (!shuf && !d.mask && ots == 1 && (a.variant & 3) == 0) {
           // Common case (every block without pixel shuffle / mask): `c` and `out` in ONE sweep over the staged tile.
           // Per-sample base pointers, per-row pointer = base + row * stride, four time steps per lane in flight:
           // the per-row 64-bit address arithmetic of the generic loops below was a ~300-cycle dependent chain in
