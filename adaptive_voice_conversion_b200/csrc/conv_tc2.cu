@@ -23,6 +23,20 @@
 //     data-gradient variant becomes three shared-memory reads.
 //   * Halo rows come straight from global memory (no dependence on the bulk copy), so long samples
 //     can be TIME-TILED (T > 144 columns: inference) for blocks without InstanceNorm.
+//   * STAGE GRANULARITY: a stage is `hs` HALF-SLABS of 8 input channels (one MMA K-step each).  Default hs = 2 (one
+//     16-channel slab of the weight pack, one contiguous bulk copy) for K >= 2 and hs = 4 for the 1x1 layers (a
+//     1104-channel in_conv makes 35 barrier round trips per tile instead of 69: 62.5 -> 60.5 us).  hs = 1 (K x 4 KB
+//     of weights per stage fetched by ONE 4-D tensor-map copy out of the [slab][tap][chunk] pack, 6 stages in flight
+//     instead of 3 for the k = 5 layers) is implemented and correct but SLOWER (AVC_T2_HS=1: 26.6 vs 23.4 us at
+//     T = 128, 48.6k vs 52.0k seg/s): the block is bound by shared-memory bandwidth, not by pipeline depth (below).
+//   * WHAT BOUNDS IT (tools/diag_ablate.py, profiles/r2_conv_ablation.txt): removing the MMAs, the copies or the store
+//     pass from the T = 128 block saves 3.3 / 2.5 / 5.8 us of 23.4 -- the parts ADD UP instead of overlapping.  A
+//     kind::tf32 SS-MMA of N = 128 fetches (128 + 128) x 32 B of operands in its 64 cycles = the whole 128 B/clk of
+//     the SM's shared memory, so while the tensor pipe runs, the copy engine's writes, the TMEM->tile pass and the
+//     store pass's reads wait (and vice versa): 1.17 MB of shared-memory traffic per sample = 9.2 K cycles, twice
+//     per CTA, plus ~10 us of launch + pipeline skeleton.  Spinning instead of suspending on the barriers, 1-D bulk
+//     copies instead of the tensor-map copy for the input rows, a 132-row plane pitch for the 1x1 layers and four
+//     independent patch warps were each measured and change nothing (<= 2 %).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -34,8 +48,9 @@ namespace avc {
 int validate_conv_desc(const avc_conv_desc* d, const char* who);
 int opt_tc_conv_v2();
 
-constexpr int T2_SLAB = 16;          // input channels per pipeline stage (2 MMA K-steps)
+constexpr int T2_SLAB = 16;          // input channels per weight-pack slab (2 MMA K-steps)
 constexpr int T2_WTAP_BYTES = 8192;  // one tap of one slab: 4 chunks x 128 co x 16 B
+constexpr int T2_HALF_BYTES = 4096;  // one tap of one half-slab (8 channels): 2 chunks x 128 co x 16 B
 constexpr int T2_MAX_STAGES = 8;
 constexpr int T2_MAX_G = 8;
 constexpr int T2_SMEM_MAX = 226 * 1024;  // 227 KB per block minus the static shared memory (barriers)
@@ -47,6 +62,9 @@ struct Tc2Args {
   int N;        // MMA N: multiple of 16, <= 256
   int srows;    // rows of one 4-channel plane of a stage (>= N + K - 1)
   int nslab, nstage;
+  int hs;       // half-slabs (8 input channels = one MMA K-step) per pipeline stage: 1, or an even number
+  int nhalf;    // half-slabs per tile (2 * nslab)
+  int nst;      // pipeline stages per tile = ceil(nhalf / hs); the last one may hold fewer half-slabs
   int TT, ntt;  // output time steps per tile, time tiles per sample
   int Ts;       // columns one sample stages for the second pass (TT, or Tout for AVC_F_FOLD)
   int P;        // chunk pitch of the staged tile in 16-byte units (== 1 mod 8)
@@ -54,10 +72,10 @@ struct Tc2Args {
   uint32_t stage_bytes, w_bytes, x_chunk_bytes;
   uint32_t off_tile, off_par, off_stat;  // byte offsets inside dynamic shared memory
   int patch;    // 1: the patch warps sit between the bulk copy and the MMAs (halo rows and/or TF32 rounding)
-  int npatch;   // patch threads that take part (32: one warp is enough for a few reflect rows; 128 otherwise)
   int variant;  // bit 0: `c` rows leave through bulk (TMA) stores; bit 1: `out` rows too (written back in place)
                 // ABLATION bits (timing probes only, results are WRONG; tools/diag_ablate.py): 16 weight copies shrunk to
-                // 1 KB, 32 no store pass, 64 no MMAs, 128 no TMEM pass, 256 no input-row copies
+                // 1 KB, 32 no store pass, 64 no MMAs, 128 no TMEM pass, 256 no input-row copies; 2048: one patch warp
+                // owns every stage (results stay correct)
   int* status;
   long long* dbg;
 };
@@ -114,7 +132,10 @@ __device__ __forceinline__ TileCoord t2_decode(const Tc2Args& a, int tile) {
 // tmx: 4-D tensor map of the input, dims (4 floats, time, sample, 4-channel chunk): ONE copy-engine instruction
 // stages [4 chunks][G samples][R rows] of a 16-channel slab -- exactly the stacked-sample operand layout -- and
 // rows / samples outside the tensor arrive as zeros (that IS the zero padding of the data-gradient convs).
-__global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a, const __grid_constant__ CUtensorMap tmx) {
+// tmw (hs == 1 only): the weight pack as a 4-D tensor (256 floats, 2 halves of a [co][4] row, 4 chunks, slab*K+tap): the box
+// (256, 2, 2, K) is one half-slab -- [tap][2 chunks][co][4] -- in one copy-engine instruction.
+__global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a, const __grid_constant__ CUtensorMap tmx,
+                                                                const __grid_constant__ CUtensorMap tmw) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // per stage: full = weights landed, fullx = input rows landed (they are small and issued first, so the patch step
   // runs while the 5x larger weight copy is still in flight), ready = patched, empty = consumed by the MMAs
@@ -129,7 +150,7 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
     for (int s = 0; s < a.nstage; ++s) {
       tc::mbar_init(&bar_full[s], 1);
       tc::mbar_init(&bar_fullx[s], 1);
-      tc::mbar_init(&bar_ready[s], (uint32_t)a.npatch);
+      tc::mbar_init(&bar_ready[s], 1);
       tc::mbar_init(&bar_empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -155,7 +176,7 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
     long long dbg0 = 0;
     for (int tile = blockIdx.x; tile < a.ntiles && ok; tile += gridDim.x) {
       const TileCoord c = t2_decode(a, tile);
-      const float* wsrc = d.w_tc + (size_t)c.mtile * a.nslab * (a.w_bytes / 4);
+      const float* wsrc = d.w_tc + (size_t)c.mtile * a.nslab * ((size_t)K * (T2_WTAP_BYTES / 4));
       const int tstart = c.t0 * S - d.pad_left;   // first input position of the staged rows (may be negative)
       // warm L2 with the NEXT tile's input rows (they usually come from HBM: a saved activation, or an input the L2
       // no longer holds), so that the latency-sensitive stage copies of that tile hit L2 like the weights do
@@ -163,25 +184,39 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
         const TileCoord cn = t2_decode(a, tile + gridDim.x);
         if (cn.b0 != c.b0 || cn.t0 != c.t0) {   // (another m-tile of the same samples reads the same rows)
           const int tsn = cn.t0 * S - d.pad_left;
-          for (int i = lane; i < a.nslab; i += 32) tc::tensor_prefetch_l2_4d(&tmx, 0, tsn, cn.b0, i * 4);
+          for (int i = lane; i < a.nst; i += 32) tc::tensor_prefetch_l2_4d(&tmx, 0, tsn, cn.b0, i * 2 * a.hs);
         }
       }
       __syncwarp();
-      for (int i = 0; i < a.nslab; ++i) {
+      for (int i = 0; i < a.nst; ++i) {
         const long long w0 = a.dbg ? clock64() : 0;
         if (!first_round) ok = __all_sync(0xffffffffu, tc::mbar_wait(&bar_empty[s], ph ^ 1u, a.status, 2));
         if (a.dbg) dbg0 += clock64() - w0;
         if (!ok) break;
         uint8_t* sw = smem + (size_t)s * a.stage_bytes;
+        const int h0 = i * a.hs, nh = min(a.hs, a.nhalf - h0);   // half-slabs [h0, h0 + nh) of the tile
         if (tc::elect_one()) {
           if (a.variant & 256) tc::mbar_arrive(&bar_fullx[s]);
           else {
-            tc::mbar_arrive_expect_tx(&bar_fullx[s], 4u * a.x_chunk_bytes);
-            tc::tensor_g2s_4d(sw + a.w_bytes, &tmx, 0, tstart, c.b0, i * 4, &bar_fullx[s]);
+            // the box always has 2*hs chunk planes; planes past Cin/4 (short last stage) arrive as zeros and are not used
+            tc::mbar_arrive_expect_tx(&bar_fullx[s], 2u * (uint32_t)a.hs * a.x_chunk_bytes);
+            tc::tensor_g2s_4d(sw + a.w_bytes, &tmx, 0, tstart, c.b0, h0 * 2, &bar_fullx[s]);
           }
-          const uint32_t wb = (a.variant & 16) ? 1024u : a.w_bytes;
-          tc::mbar_arrive_expect_tx(&bar_full[s], wb);
-          tc::bulk_g2s(sw, wsrc + (size_t)i * (a.w_bytes / 4), wb, &bar_full[s]);
+          if (a.hs == 1) {
+            const uint32_t wb = (uint32_t)K * T2_HALF_BYTES;
+            if (a.variant & 16) {
+              tc::mbar_arrive_expect_tx(&bar_full[s], 1024u);
+              tc::bulk_g2s(sw, wsrc, 1024u, &bar_full[s]);
+            } else {
+              tc::mbar_arrive_expect_tx(&bar_full[s], wb);
+              tc::tensor_g2s_4d(sw, &tmw, 0, 0, (h0 & 1) * 2, (c.mtile * a.nslab + (h0 >> 1)) * K, &bar_full[s]);
+            }
+          } else {
+            const uint32_t wfull = (uint32_t)(nh >> 1) * (uint32_t)K * T2_WTAP_BYTES;   // whole slabs, contiguous in the pack
+            const uint32_t wb = (a.variant & 16) ? 1024u : wfull;
+            tc::mbar_arrive_expect_tx(&bar_full[s], wb);
+            tc::bulk_g2s(sw, wsrc + (size_t)(h0 >> 1) * ((size_t)K * (T2_WTAP_BYTES / 4)), wb, &bar_full[s]);
+          }
         }
         __syncwarp();
         if (++s == a.nstage) { s = 0; ph ^= 1u; first_round = false; }
@@ -196,7 +231,9 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
     const uint32_t d_hi = tc::sdesc_hi(128);
     const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
     const uint32_t smem0 = tc::smem_u32(smem);
-    const uint32_t ks_b = 2u * (a.x_chunk_bytes >> 4);
+    const uint32_t ks_b = 2u * (a.x_chunk_bytes >> 4);                       // B operand: next half-slab = 2 chunk planes on
+    const uint32_t tap_a = (a.hs == 1 ? T2_HALF_BYTES : T2_WTAP_BYTES) >> 4;   // A operand: next tap
+    const uint32_t slab_a = (uint32_t)K * (T2_WTAP_BYTES >> 4);                // A operand: next slab (hs > 1)
     int s = 0;
     uint32_t ph = 0;
     bool ok = true;
@@ -210,7 +247,7 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
       if (!ok) break;
       tc::tc_fence_after();
       const uint32_t dcol = tb + buf * 256u;
-      for (int i = 0; i < a.nslab; ++i) {
+      for (int i = 0; i < a.nst; ++i) {
         const long long w0 = a.dbg ? clock64() : 0;
         ok = __all_sync(0xffffffffu, tc::mbar_wait(a.patch ? &bar_ready[s] : &bar_fullx[s], ph, a.status, 3) &&
                                          tc::mbar_wait(&bar_full[s], ph, a.status, 3));
@@ -220,22 +257,23 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
         tc::tc_fence_after();
         const uint32_t sw = smem0 + (uint32_t)s * a.stage_bytes;
         const uint32_t a_lo0 = tc::sdesc_lo(sw, 2048), b_lo0 = tc::sdesc_lo(sw + a.w_bytes, a.x_chunk_bytes);
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
+        const int nh = min(a.hs, a.nhalf - i * a.hs);
+        for (int e = 0; e < nh; ++e) {   // half-slab e of the stage: one K-step of 8 input channels per tap
           if (a.variant & 64) break;
-          uint64_t a_desc = tc::sdesc64(a_lo0 + (uint32_t)ks * (4096 >> 4), d_hi);
-          uint64_t b_desc = tc::sdesc64(b_lo0 + (uint32_t)ks * ks_b, d_hi);
+          const uint32_t a_off = a.hs == 1 ? 0u : (uint32_t)(e >> 1) * slab_a + (uint32_t)(e & 1) * (T2_HALF_BYTES >> 4);
+          uint64_t a_desc = tc::sdesc64(a_lo0 + a_off, d_hi);
+          uint64_t b_desc = tc::sdesc64(b_lo0 + (uint32_t)e * ks_b, d_hi);
           if (K == 5) {
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
-              tc::mma_tf32_elect(dcol, a_desc, b_desc, idesc, ((uint32_t)i | (uint32_t)ks | (uint32_t)j) ? 1u : 0u);
-              a_desc += (uint64_t)(T2_WTAP_BYTES >> 4);
+              tc::mma_tf32_elect(dcol, a_desc, b_desc, idesc, ((uint32_t)i | (uint32_t)e | (uint32_t)j) ? 1u : 0u);
+              a_desc += (uint64_t)tap_a;
               b_desc += 1u;
             }
           } else {
             for (int j = 0; j < K; ++j) {
-              tc::mma_tf32_elect(dcol, a_desc, b_desc, idesc, ((uint32_t)i | (uint32_t)ks | (uint32_t)j) ? 1u : 0u);
-              a_desc += (uint64_t)(T2_WTAP_BYTES >> 4);
+              tc::mma_tf32_elect(dcol, a_desc, b_desc, idesc, ((uint32_t)i | (uint32_t)e | (uint32_t)j) ? 1u : 0u);
+              a_desc += (uint64_t)tap_a;
               b_desc += 1u;
             }
           }
@@ -255,7 +293,7 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
       o[5] = dbg0; o[6] = dbg1; o[7] = dbg2;
     }
   } else if (warp >= 4 && warp < 8) {
-    // ================================================================ patch warps (128 threads)
+    // ================================================================ patch warps (4 warps, ROUND ROBIN over the stages)
     // (a) reflect padding: the copy engine delivered zeros for the rows outside the sample; they are overwritten
     //     with their mirror rows, taken from the staged rows of the same sample (from global memory only when a
     //     time-tiled sample's mirror row lies outside the tile);
@@ -263,84 +301,110 @@ __global__ void __launch_bounds__(512, 1) conv_block_tc2_kernel(const Tc2Args a,
     //     stream stays full fp32 like the reference's activations): every row is rounded to nearest in place, so
     //     that the tensor core's truncation is exact.
     // a.patch == 0 (zero padding or K = 1, pre-rounded input): these warps idle, the MMAs wait on the copies directly.
-    const int ptid = tid - 128;
+    // One patch step is a dependent chain (barrier wake-up, shared-memory load, store, proxy fence, arrive) of
+    // ~400-1000 cycles whatever the stage holds, and with ONE owner of all stages it was the serial resource of the
+    // whole pipeline (tools/diag_ablate.py: the empty pipeline cost ~740 cycles per stage, 2x the stages = 2x the
+    // time).  Warp w therefore owns the shared-memory STAGES s % npw == w outright (wait, round, mirror, fence, ONE
+    // arrive): up to four patch steps are in flight and none of them synchronises with another warp.  Ownership goes
+    // by stage, not by iteration: every phase of a stage's barrier is then seen by the same warp in order (a warp
+    // that skipped a phase could run a whole ring revolution ahead, and a parity wait on a barrier that is still one
+    // phase behind returns immediately -- the false positive every mbarrier pipeline has to exclude).
+    const int pw = warp - 4;
     const bool rnd = !(d.flags & AVC_F_IN_TF32);
     const bool refl = d.pad_mode == AVC_PAD_REFLECT;
+    const int npw = (a.variant & 2048) ? 1 : min(4, a.nstage);   // probe bit 2048: a single patch warp owns every stage (the previous structure)
     int s = 0;
     uint32_t ph = 0;
     bool ok = true;
     long long dbg0 = 0, dbg1 = 0;
-    for (int tile = blockIdx.x; a.patch && ptid < a.npatch && tile < a.ntiles && ok; tile += gridDim.x) {
+    for (int tile = blockIdx.x; a.patch && pw < npw && tile < a.ntiles && ok; tile += gridDim.x) {
       const TileCoord c = t2_decode(a, tile);
       const int pbeg = c.t0 * S - d.pad_left;
       const int nr = (c.tw - 1) * S + K;  // rows one sample needs
       const int p_lo = max(0, pbeg), p_hi = min(d.Tin, pbeg + a.R);   // input positions present in the staged rows
       const int ncopy = max(0, min(p_hi, pbeg + nr) - p_lo), r_lo = p_lo - pbeg;
       const int nh = refl ? nr - ncopy : 0;
-      // The halo assignment of a thread is the same for every slab of the tile: resolve it ONCE (the index arithmetic
-      // -- two runtime divisions and the mirror position -- was a ~600-cycle dependent chain in front of every stage).
-      // Thread e handles (sample g, halo row h, plane q); more than 128 entries fall back to the generic loop.
-      const int nent = c.nsamp * nh * 4;
-      int h_dst = -1, h_src = -1, h_glob = -1;   // float4 offsets inside the stage's x region; global source position
-      if (ptid < nent) {   // (nent <= npatch entries are resolved here, the rest in the generic loop below)
-        const int q = ptid & 3, r = ptid >> 2;
-        const int g = r / nh, h = r - g * nh;
-        const int u = h < r_lo ? h : h + ncopy;
-        const int p = src_pos(pbeg + u, d.Tin, AVC_PAD_REFLECT, 1);
-        h_dst = q * a.srows + g * a.R + u;
-        if (p >= p_lo && p < p_hi) h_src = q * a.srows + g * a.R + (p - pbeg);
-        else if (p >= 0) h_glob = p;
-      }
-      const int hq = ptid & 3, hg = (ptid >> 2) / (nh > 0 ? nh : 1);
-      for (int i = 0; i < a.nslab && ok; ++i) {
-        const long long w0 = a.dbg ? clock64() : 0;
-        ok = tc::mbar_wait(&bar_fullx[s], ph, a.status, 4);
-        const long long w1 = a.dbg ? clock64() : 0;
-        dbg0 += w1 - w0;
-        if (!ok) break;
-        float4* sx = reinterpret_cast<float4*>(smem + (size_t)s * a.stage_bytes + a.w_bytes);
-        bool wrote = false;
-        if (rnd) {
-          // every row of every plane (halo / gap rows included: rounding them again is harmless): no index arithmetic
-          const int nrow = c.nsamp * a.R;
-          for (int e = ptid; e < nrow * 4; e += 128) {   // (rounding always runs with all 128 patch threads)
-            float4* p = sx + (size_t)(e & 3) * a.srows + (e >> 2);
-            *p = t2_round4(*p);
-          }
-          wrote = true;
-          if (nh > 0) t2_bar_sync(1, 128);   // the reflect rows below copy ROUNDED rows
-        }
-        if (h_dst >= 0) {
-          float4 v = zero4();
-          if (h_src >= 0) v = sx[h_src];
-          else if (h_glob >= 0) {
-            v = ldg4(d.in + (size_t)(c.b0 + hg) * d.in_bstride + ((size_t)(i * 4 + hq) * d.Tin + h_glob) * 4);
-            if (rnd) v = t2_round4(v);
-          }
-          sx[h_dst] = v;
-          wrote = true;
-        }
-        for (int e = ptid + a.npatch; e < nent; e += a.npatch) {   // more halo entries than patch threads (large K x G): generic path
-          const int q = e & 3, r = e >> 2;
+      // The halo assignment of a lane is the same for every stage of the tile: resolve it ONCE (the index arithmetic
+      // -- runtime divisions and the mirror position -- was a ~600-cycle dependent chain in front of every stage).
+      // Entry e = lane + 32 j (j < 4) is (sample g, halo row h, plane q); more than 128 entries use the generic loop.
+      const int npl = 2 * a.hs;                  // 4-channel planes of a stage
+      const int nent = c.nsamp * nh * npl;
+      int h_dst[4], h_src[4], h_glob[4], h_q[4], h_g[4];   // float4 offsets inside the stage's x region; global source
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = lane + 32 * j;
+        h_dst[j] = h_src[j] = h_glob[j] = -1;
+        h_q[j] = h_g[j] = 0;
+        if (e < nent) {
+          const int q = e % npl, r = e / npl;
           const int g = r / nh, h = r - g * nh;
           const int u = h < r_lo ? h : h + ncopy;
           const int p = src_pos(pbeg + u, d.Tin, AVC_PAD_REFLECT, 1);
-          float4 v = zero4();
-          if (p >= p_lo && p < p_hi) v = sx[(size_t)q * a.srows + g * a.R + (p - pbeg)];
-          else if (p >= 0) {
-            v = ldg4(d.in + (size_t)(c.b0 + g) * d.in_bstride + ((size_t)(i * 4 + q) * d.Tin + p) * 4);
-            if (rnd) v = t2_round4(v);
-          }
-          sx[(size_t)q * a.srows + g * a.R + u] = v;
-          wrote = true;
+          h_dst[j] = q * a.srows + g * a.R + u;
+          h_q[j] = q;
+          h_g[j] = g;
+          if (p >= p_lo && p < p_hi) h_src[j] = q * a.srows + g * a.R + (p - pbeg);
+          else if (p >= 0) h_glob[j] = p;
         }
-        if (wrote) tc::fence_proxy_async_smem();   // only writers pay for the proxy fence
-        tc::mbar_arrive(&bar_ready[s]);
-        if (a.dbg) dbg1 += clock64() - w1;
+      }
+      for (int i = 0; i < a.nst && ok; ++i) {
+        if (s % npw == pw) {
+          const long long w0 = a.dbg ? clock64() : 0;
+          ok = tc::mbar_wait(&bar_fullx[s], ph, a.status, 4);
+          const long long w1 = a.dbg ? clock64() : 0;
+          dbg0 += w1 - w0;
+          if (!ok) break;
+          float4* sx = reinterpret_cast<float4*>(smem + (size_t)s * a.stage_bytes + a.w_bytes);
+          bool wrote = false;
+          if (rnd) {
+            // every row of every plane (halo / gap rows included: rounding them again is harmless): the planes are
+            // contiguous, so the sweep is a linear, conflict-free walk with no index arithmetic; 4 loads in flight
+            const int nf4 = npl * a.srows;
+            int e = lane;
+            for (; e + 96 < nf4; e += 128) {
+              const float4 v0 = sx[e], v1 = sx[e + 32], v2 = sx[e + 64], v3 = sx[e + 96];
+              sx[e] = t2_round4(v0); sx[e + 32] = t2_round4(v1); sx[e + 64] = t2_round4(v2); sx[e + 96] = t2_round4(v3);
+            }
+            for (; e < nf4; e += 32) sx[e] = t2_round4(sx[e]);
+            wrote = true;
+            if (nh > 0) __syncwarp();   // the reflect rows below copy ROUNDED rows
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (h_dst[j] >= 0) {
+              float4 v = zero4();
+              if (h_src[j] >= 0) v = sx[h_src[j]];
+              else if (h_glob[j] >= 0 && (i * npl + h_q[j]) * 4 < d.Cin) {
+                v = ldg4(d.in + (size_t)(c.b0 + h_g[j]) * d.in_bstride + ((size_t)(i * npl + h_q[j]) * d.Tin + h_glob[j]) * 4);
+                if (rnd) v = t2_round4(v);
+              }
+              sx[h_dst[j]] = v;
+              wrote = true;
+            }
+          }
+          for (int e = lane + 128; e < nent; e += 32) {   // more than 128 halo entries (large K x G): generic path
+            const int q = e % npl, r = e / npl;
+            const int g = r / nh, h = r - g * nh;
+            const int u = h < r_lo ? h : h + ncopy;
+            const int p = src_pos(pbeg + u, d.Tin, AVC_PAD_REFLECT, 1);
+            float4 v = zero4();
+            if (p >= p_lo && p < p_hi) v = sx[(size_t)q * a.srows + g * a.R + (p - pbeg)];
+            else if (p >= 0 && (i * npl + q) * 4 < d.Cin) {
+              v = ldg4(d.in + (size_t)(c.b0 + g) * d.in_bstride + ((size_t)(i * npl + q) * d.Tin + p) * 4);
+              if (rnd) v = t2_round4(v);
+            }
+            sx[(size_t)q * a.srows + g * a.R + u] = v;
+            wrote = true;
+          }
+          if (wrote) tc::fence_proxy_async_smem();   // only writers pay for the proxy fence
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&bar_ready[s]);
+          if (a.dbg) dbg1 += clock64() - w1;
+        }
         if (++s == a.nstage) { s = 0; ph ^= 1u; }
       }
     }
-    if (a.dbg && ptid == 0) {
+    if (a.dbg && tid == 128) {
       long long* o = a.dbg + (size_t)blockIdx.x * 16;
       o[3] = dbg0; o[4] = dbg1;
     }
@@ -787,7 +851,7 @@ int t2_plan(const avc_conv_desc* d, Tc2Args& a) {
   a.d = *d;
   if (!a.d.res) a.d.res_mode = AVC_RES_NONE;
   a.nslab = d->Cin / T2_SLAB;
-  a.w_bytes = (uint32_t)K * T2_WTAP_BYTES;
+  a.nhalf = 2 * a.nslab;
   a.mtiles = cdiv(d->Cout, 128);
   const int ncol_full = (d->Tout - 1) * S + 1;
   if (d->pad_mode == AVC_PAD_REFLECT && d->Tin <= d->pad_left) return AVC_ERR_UNSUPPORTED;   // no mirror row to copy
@@ -815,7 +879,7 @@ int t2_plan(const avc_conv_desc* d, Tc2Args& a) {
     if (span + (ncol + 15) / 16 * 16 > 256) break;
     const int N = (span + ncol + 15) / 16 * 16;
     const int ntiles = cdiv(d->B, G) * a.ntt * a.mtiles;
-    const double mma = (double)a.nslab * 2 * K * (N / 2 > 40 ? N / 2 : 40);
+    const double mma = (double)a.nhalf * K * (N / 2 > 40 ? N / 2 : 40);
     const double cost = (double)cdiv(ntiles, sms) * (3000.0 + mma);
     if (cost <= best) { best = cost; bestG = G; }
   }
@@ -824,9 +888,6 @@ int t2_plan(const avc_conv_desc* d, Tc2Args& a) {
   a.N = ((a.G - 1) * a.R + ncol + 15) / 16 * 16;
   a.srows = a.G * a.R;   // one plane of the tensor-copy box: [G samples][R rows] of 16 bytes
   a.x_chunk_bytes = (uint32_t)a.srows * 16u;
-  // an N-column MMA reads up to N + K - 1 rows of the last plane, at most 15 + K rows past its end (garbage columns):
-  // keep that inside the stage
-  a.stage_bytes = (a.w_bytes + 4u * a.x_chunk_bytes + 32u * 16u + 1023u) / 1024u * 1024u;
   a.ngroups = cdiv(d->B, a.G);
   a.ntiles = a.ngroups * a.ntt * a.mtiles;
   // staged tile: 32 chunks, pitch == 1 mod 8 sixteen-byte units
@@ -835,9 +896,29 @@ int t2_plan(const avc_conv_desc* d, Tc2Args& a) {
   const uint32_t tile_bytes = 32u * (uint32_t)a.P * 16u;
   const uint32_t par_bytes = 3u * (uint32_t)a.G * 128u * 4u, stat_bytes = 2u * (uint32_t)a.G * 128u * 8u;
   const uint32_t tail = tile_bytes + par_bytes + stat_bytes;
-  int nstage = (int)((T2_SMEM_MAX - (int)tail) / (int)a.stage_bytes);
+  // Half-slabs per stage (see the header): one slab for K >= 2; the 1x1 layers have tiny half-slabs and want fewer
+  // barrier round trips (hs = 4, falling back to one slab per stage when the tile leaves no room for three such stages).
+  static int hs_env = -1;
+  if (hs_env < 0) {
+    const char* e = getenv("AVC_T2_HS");
+    hs_env = e ? atoi(e) : 0;
+  }
+  int hs = K >= 2 ? 2 : 4;
+  if (hs_env > 0) hs = hs_env == 1 ? 1 : (hs_env + 1) / 2 * 2;
+  if (hs > a.nhalf) hs = a.nhalf;
+  int nstage = 0;
+  for (;; hs = hs > 2 ? hs - 2 : 1) {
+    a.hs = hs;
+    a.w_bytes = hs == 1 ? (uint32_t)K * T2_HALF_BYTES : (uint32_t)(hs / 2) * (uint32_t)K * T2_WTAP_BYTES;
+    // an N-column MMA reads up to N + K - 1 rows of the last plane, at most 15 + K rows past its end (garbage columns):
+    // keep that inside the stage
+    a.stage_bytes = (a.w_bytes + 2u * (uint32_t)hs * a.x_chunk_bytes + 32u * 16u + 1023u) / 1024u * 1024u;
+    nstage = (int)((T2_SMEM_MAX - (int)tail) / (int)a.stage_bytes);
+    if (nstage >= 3 || hs == 1) break;
+  }
   if (nstage > T2_MAX_STAGES) nstage = T2_MAX_STAGES;
   if (nstage < 2) return AVC_ERR_UNSUPPORTED;
+  a.nst = cdiv(a.nhalf, a.hs);
   a.nstage = nstage;
   a.off_tile = (uint32_t)nstage * a.stage_bytes;
   a.off_par = a.off_tile + tile_bytes;
@@ -862,10 +943,8 @@ int conv_block_tc2_launch(const avc_conv_desc* d, int* status, void* stream) {
   a.status = status;
   a.dbg = g_tc2_dbg;
   a.patch = (!(d->flags & AVC_F_IN_TF32) || (d->pad_mode == AVC_PAD_REFLECT && d->K > 1)) ? 1 : 0;
-  // a few reflect rows of a pre-rounded input: one warp does it (three fewer warps polling the stage barriers)
-  a.npatch = ((d->flags & AVC_F_IN_TF32) && a.G * (d->K - 1) * 4 <= 32) ? 32 : 128;
   a.variant = t2_variant();
-  CUtensorMap tmx;
+  CUtensorMap tmx, tmw;
   {
     PFN_tmap_encode enc = tmap_encode_fn();
     if (!enc) {
@@ -874,7 +953,7 @@ int conv_block_tc2_launch(const avc_conv_desc* d, int* status, void* stream) {
     }
     const cuuint64_t gdim[4] = {4, (cuuint64_t)d->Tin, (cuuint64_t)d->B, (cuuint64_t)(d->Cin / 4)};
     const cuuint64_t gstr[3] = {16, (cuuint64_t)d->in_bstride * 4u, (cuuint64_t)d->Tin * 16u};
-    const cuuint32_t box[4] = {4, (cuuint32_t)a.R, (cuuint32_t)a.G, 4};
+    const cuuint32_t box[4] = {4, (cuuint32_t)a.R, (cuuint32_t)a.G, (cuuint32_t)(2 * a.hs)};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUresult r = enc(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)d->in, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -882,6 +961,21 @@ int conv_block_tc2_launch(const avc_conv_desc* d, int* status, void* stream) {
       set_error("avc_conv_block_tc: cuTensorMapEncodeTiled failed (%d) for Tin=%d B=%d Cin=%d bstride=%lld box R=%d G=%d", (int)r, d->Tin, d->B,
                 d->Cin, (long long)d->in_bstride, a.R, a.G);
       return AVC_ERR_CUDA;
+    }
+    tmw = tmx;   // unused unless hs == 1
+    if (a.hs == 1) {
+      if ((uintptr_t)d->w_tc & 15u) return AVC_ERR_UNSUPPORTED;
+      // the weight pack [mtile][slab][tap][chunk 4][co 128][4] as rows of 2 KB, each split into two 1 KB halves (a box
+      // dimension holds at most 256 elements): (256 floats, half, chunk, slab*K + tap)
+      const cuuint64_t wdim[4] = {256, 2, 4, (cuuint64_t)a.mtiles * (cuuint64_t)a.nslab * (cuuint64_t)d->K};
+      const cuuint64_t wstr[3] = {1024, 2048, 8192};
+      const cuuint32_t wbox[4] = {256, 2, 2, (cuuint32_t)d->K};
+      const CUresult rw = enc(&tmw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)d->w_tc, wdim, wstr, wbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (rw != CUDA_SUCCESS) {
+        set_error("avc_conv_block_tc: cuTensorMapEncodeTiled failed (%d) for the weight pack K=%d Cin=%d Cout=%d", (int)rw, d->K, d->Cin, d->Cout);
+        return AVC_ERR_CUDA;
+      }
     }
   }
   const int smem = (int)(a.off_stat + 2u * (uint32_t)a.G * 128u * 8u);
@@ -895,7 +989,7 @@ int conv_block_tc2_launch(const avc_conv_desc* d, int* status, void* stream) {
     attr_done = true;
   }
   const int grid = a.ntiles < t2_num_sms() ? a.ntiles : t2_num_sms();
-  AVC_LAUNCH(conv_block_tc2_kernel, grid, 512, smem, (cudaStream_t)stream, a, tmx);
+  AVC_LAUNCH(conv_block_tc2_kernel, grid, 512, smem, (cudaStream_t)stream, a, tmx, tmw);
   AVC_CHECK_LAUNCH("conv_block_tc2");
   return AVC_OK;
 }

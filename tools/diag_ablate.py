@@ -15,7 +15,11 @@ eng = Engine(default_config(80), dev)
 B = int(os.environ.get("DIAG_B", "256"))
 PROBES = [(0, "full kernel"), (16, "weights 1 KB/stage"), (256, "no input rows"), (16 + 256, "no copies"), (64, "no MMAs"),
           (128, "no TMEM pass"), (32, "no store pass"), (32 + 128, "no epilogue"), (16 + 256 + 32 + 128, "MMAs only"),
-          (64 + 32 + 128, "copies only"), (16 + 256 + 64 + 128, "stores only"), (16 + 256 + 64 + 32 + 128, "empty pipeline")]
+          (64 + 32 + 128, "copies only"), (16 + 256 + 64 + 128, "stores only"), (16 + 256 + 64 + 32 + 128, "empty pipeline"),
+          (2048, "full, one patch warp"), (2048 + 496, "empty, one patch warp")]
+if os.environ.get("DIAG_PROBES"):
+    keep = {int(v) for v in os.environ["DIAG_PROBES"].split(",")}
+    PROBES = [p for p in PROBES if p[0] in keep]
 SHAPES = [(128, 128, 5, 128, dict(norm=True, relu=True), "conv5 T128 IN"), (128, 128, 5, 32, dict(norm=True, relu=True), "conv5 T32 IN"),
           (1104, 128, 1, 128, dict(norm=True, relu=True), "in_conv 1104")]
 
