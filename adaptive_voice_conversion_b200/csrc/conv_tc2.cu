@@ -28,7 +28,11 @@
 //     1104-channel in_conv makes 35 barrier round trips per tile instead of 69: 62.5 -> 60.5 us).  hs = 1 (K x 4 KB
 //     of weights per stage fetched by ONE 4-D tensor-map copy out of the [slab][tap][chunk] pack, 6 stages in flight
 //     instead of 3 for the k = 5 layers) is implemented and correct but SLOWER (AVC_T2_HS=1: 26.6 vs 23.4 us at
-//     T = 128, 48.6k vs 52.0k seg/s): the block is bound by shared-memory bandwidth, not by pipeline depth (below).
+//     T = 128, 48.6k vs 52.0k seg/s; K bulk copies of 4 KB instead of the tensor-map copy: 27.6 us): every stage
+//     iteration costs ~450-600 cycles of barrier round trips whatever it carries, and hs = 1 doubles their number.
+//     Depth does matter at equal stage size: capping the k = 5 layers at 2 stages (AVC_T2_NSTAGE=2) costs 4.1 us at
+//     T = 128 (23.9 -> 28.0), i.e. the main loop runs at ~(3 K cycles ring latency) / (stages in flight); the 70 KB
+//     epilogue tile is what keeps the k = 5 layers at 3 stages of 49 KB.
 //   * WHAT BOUNDS IT (tools/diag_ablate.py, profiles/r2_conv_ablation.txt): removing the MMAs, the copies or the store
 //     pass from the T = 128 block saves 3.3 / 2.5 / 5.8 us of 23.4 -- the parts ADD UP instead of overlapping.  A
 //     kind::tf32 SS-MMA of N = 128 fetches (128 + 128) x 32 B of operands in its 64 cycles = the whole 128 B/clk of
@@ -917,6 +921,14 @@ int t2_plan(const avc_conv_desc* d, Tc2Args& a) {
     if (nstage >= 3 || hs == 1) break;
   }
   if (nstage > T2_MAX_STAGES) nstage = T2_MAX_STAGES;
+  {
+    static int cap = -1;   // probe: AVC_T2_NSTAGE caps the pipeline depth (how does the main loop scale with stages in flight?)
+    if (cap < 0) {
+      const char* e = getenv("AVC_T2_NSTAGE");
+      cap = e ? atoi(e) : 0;
+    }
+    if (cap >= 2 && nstage > cap) nstage = cap;
+  }
   if (nstage < 2) return AVC_ERR_UNSUPPORTED;
   a.nst = cdiv(a.nhalf, a.hs);
   a.nstage = nstage;
