@@ -7,6 +7,11 @@ gradient buffer per iteration; the 1/world scale is folded into the clip/Adam ke
 the order backward -> all-reduce -> global-norm clip -> Adam matches a single-process
 step on the concatenated batch.
 
+The speaker encoder and the content encoder are independent until the decoder (model.py:381-385), and so
+are their backward passes after it: ``_fwd_bwd`` runs the speaker branch on a second stream (fork / join with
+events, also inside the captured graph), so the two chains of ~100 dependent launches each fill each other's
+launch-boundary bubbles and the SMs the small-T layers leave idle (AVC_OVERLAP=0: one stream).
+
 ``capture()`` records the step once into CUDA graphs (static shapes) and ``step()`` replays
 them: one graph for the whole step in a single process; with N > 1 graph A = zero-grad +
 forward + loss + backward, graph B = norm + Adam + weight re-pack, and the all-reduce runs
@@ -14,6 +19,7 @@ between them.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -47,6 +53,8 @@ class FusedTrainer:
         self.eng.pack_weights(self.P, need_dgrad=True)
         self.eng.prepare_tables(self.P, self.G)   # before any CUDA-graph capture
         self.eng.prepare_wgrad_acc(self.P, self.G)
+        self.overlap = os.environ.get("AVC_OVERLAP", "1") == "1"
+        self._side = torch.cuda.Stream(self.dev) if self.overlap else None
         self._lambda_kl = None
         self._hp_key = None
         self._static_eps = None
@@ -55,13 +63,22 @@ class FusedTrainer:
 
     # ------------------------------------------------------------------ pieces
     def _fwd_bwd(self, x: torch.Tensor, eps: Optional[torch.Tensor]):
-        eng, P, G, st = self.eng, self.P, self.G, None
+        eng, P, G = self.eng, self.P, self.G
+        main, side = torch.cuda.current_stream(self.dev), self._side
         self.opt.zero_grad()
-        emb, cs = eng.speaker_fwd(P, x, True)
+        # ---- forward: speaker branch || content branch (both only read x), joined in front of the decoder
+        if side is not None:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                emb, cs = eng.speaker_fwd(P, x, True)
+        else:
+            emb, cs = eng.speaker_fwd(P, x, True)
         mu4, ls4, ce = eng.content_fwd(P, x, True)
         if eps is None:
             eps = torch.randn((mu4.B, mu4.C, mu4.T), dtype=torch.float32, device=self.dev)
         mu, ls, z4 = eng.reparam_fwd(mu4, ls4, eps)
+        if side is not None:
+            main.wait_stream(side)
         dec4, cd = eng.decoder_fwd(P, z4, emb, True)
         dec = eng.unpack_a4(dec4)
         ddec, dmu, dls = torch.empty_like(dec), torch.empty_like(mu), torch.empty_like(ls)
@@ -72,9 +89,19 @@ class FusedTrainer:
         ddec4 = A4.empty(dec4.B, dec4.C, dec4.T, self.dev)
         eng.pack_a4(ddec, ddec4)
         dz4, demb = eng.decoder_bwd(P, G, cd, ddec4)
+        # ---- backward: the two encoders again in parallel (disjoint parameters, disjoint gradient buffers)
+        if side is not None:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                eng.speaker_bwd(P, G, cs, demb)
         dmu4, dls4 = eng.reparam_bwd(dz4, ls4, eps, dmu, dls)
         eng.content_bwd(P, G, ce, dmu4, dls4)
-        eng.speaker_bwd(P, G, cs, demb)
+        if side is not None:
+            main.wait_stream(side)
+        else:
+            eng.speaker_bwd(P, G, cs, demb)
+        # (every tensor the side stream touched -- x, emb, demb, cs -- is a local that lives until this function
+        # returns, i.e. until after the join: the caching allocator cannot hand its memory to the other stream early)
         eng.flush_wgrad()   # no-op unless weight gradients were accumulated in place (AVC_WGRAD_ACC=1)
         return mu, ls, emb, dec
 

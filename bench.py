@@ -217,28 +217,39 @@ def dominant_kernel_roofline(dev, batch):
     xs = [A4.empty(batch, Cc, T, dev) for _ in range(nbuf)]
     for a in xs:
         a.t.normal_()
-    for i in range(3):
-        eng.conv(P, "r", xs[i % nbuf], norm=True, relu=True, train=True)
-    torch.cuda.synchronize(dev)
     # the kernel is shorter than a Python launch: time a CUDA graph of `reps` back-to-back launches
     # (rotating >L2 inputs) with events on the launching stream
     reps = 20
     side = torch.cuda.Stream(dev)
-    graph = torch.cuda.CUDAGraph()
-    keep = []
-    with torch.cuda.stream(side):
-        with torch.cuda.graph(graph, stream=side):
-            for i in range(reps):
-                keep.append(eng.conv(P, "r", xs[i % nbuf], norm=True, relu=True, train=True))
-        graph.replay()
-        side.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(side)
-        for _ in range(3):
+
+    def timed():
+        for i in range(3):
+            eng.conv(P, "r", xs[i % nbuf], norm=True, relu=True, train=True)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        keep = []
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                for i in range(reps):
+                    keep.append(eng.conv(P, "r", xs[i % nbuf], norm=True, relu=True, train=True))
             graph.replay()
-        e1.record(side)
-        side.synchronize()
-    avg_ms = e0.elapsed_time(e1) / (3 * reps)
+            side.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(side)
+            for _ in range(3):
+                graph.replay()
+            e1.record(side)
+            side.synchronize()
+        return e0.elapsed_time(e1) / (3 * reps)
+
+    # the block as the FIRST conv of a ConvBlock pair sees it: fp32 residual-stream input, rounded to TF32 while staged
+    avg_ms = timed()
+    # ... and as the SECOND conv sees it: input already TF32-exact (written by a rounding producer), no rounding pass
+    avg_ms_pre = None
+    if eng.precision == "tf32":
+        for a in xs:
+            a.tf32 = True
+        avg_ms_pre = timed()
     flops = 2.0 * Cc * Cc * K * T * batch
     alg_bytes = (Cc * T * batch * 4) * 3 + w.numel() * 4  # read x, write c (saved for bwd) and y, read weights
     peaks = {}
@@ -267,10 +278,13 @@ def dominant_kernel_roofline(dev, batch):
     # but ~7.7 us of HBM time for its algorithmic bytes (x in once, c and y out once, weights) -> HBM-bound.
     return {"bound": "hbm", "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm, "traffic": traffic,
             "traffic_source": traffic_src,
-            "kernel": ("conv_block_tc_kernel (tcgen05 TF32: fused reflect-pad conv k5 128->128 + InstanceNorm + ReLU, saves c)" if eng.precision == "tf32"
+            "kernel": ("conv_block_tc2_kernel (persistent tcgen05 TF32: fused reflect-pad conv k5 128->128 + InstanceNorm + ReLU, saves c)" if eng.precision == "tf32"
                        else "conv_block_fwd_kernel<5,1,128,128> (same block, fp32 FFMA path)"),
             "shape": f"B={batch}, 128->128, k=5, T={T}",
-            "avg_launch_ms": avg_ms, "alg_bytes_per_launch": alg_bytes, "alg_flops_per_launch": flops,
+            "avg_launch_ms": avg_ms, "avg_launch_ms_prerounded_input": avg_ms_pre,
+            "input": "fp32 (the residual stream: rounded to TF32 while staged); avg_launch_ms_prerounded_input = the same launch on a TF32-exact input "
+                     "(the second conv of every block), not used for frac",
+            "alg_bytes_per_launch": alg_bytes, "alg_flops_per_launch": flops,
             "alg_bytes_note": "read x 16.8 MB + write c (saved for backward) 16.8 MB + write y 16.8 MB + weights 0.33 MB",
             "tensor_tflops": tf, "tensor_frac_of_bf16_peak": tf / peak_tf, "tensor_frac_of_tf32_rate": tf / (0.5 * peak_tf),
             "peak_source": src, "precision": eng.precision,
@@ -369,6 +383,8 @@ def run_b200(args):
             "dtype": "tf32" if precision == "tf32" else "f32",
             "data": "synthetic N(0,1) segments, random-init weights",
             "config": dict(workload_config(args, world), cuda_graph=not args.no_graph,
+                           streams="2 (speaker-encoder branch forked beside the content-encoder branch, forward and backward)"
+                           if os.environ.get("AVC_OVERLAP", "1") == "1" else "1",
                            l2="per-step working set (~1.5 GB saved activations) >> 126 MB L2; no explicit flush"),
             "timing": {"windows": NWIN, "steps_per_window": K, "reported": "median window",
                        "window_ms": win, "e2e_window_ms": win_e2e},
