@@ -105,6 +105,8 @@ class Engine:
         # epilogue (AVC_F_FOLD) instead of a separate avc_fold_add_fwd pass
         self.fold_fused = os.environ.get("AVC_FOLD_FUSED", "1" if L.DEFAULT_FOLD_FUSED else "0") == "1"
         self._wg_acc = None
+        self.wgrad_stream = None     # set by FusedTrainer around a step: weight gradients fork onto this stream
+        self._wg_keep = []
         self.tc_conv_v2 = bool(self.lib.avc_get_option(b"tc_conv_v2"))
         # the data-gradient conv of a block also runs the upstream block's norm backward (AVC_F_NORMBWD); off = one
         # avc_norm_bwd launch per block
@@ -251,8 +253,7 @@ class Engine:
 
                 def buf(k, n):
                     if k not in slot or slot[k].numel() != n:
-                        slot[k] = self.empty(n)
-                        tables.clear()   # cached tables may point at the buffer just replaced
+                        slot[k] = self.empty(n)   # (tables that pointed at a replaced buffer fail the liveness check above)
                     used[(name, k)] = slot[k].data_ptr()
                     return slot[k].data_ptr()
                 if simt:
@@ -405,8 +406,29 @@ class Engine:
             self._ck(self.lib.avc_wgrad_acc_flush(acc["items"].data_ptr(), acc["n"], acc["max_units"], self.stream), "wgrad_acc_flush")
             acc["dirty"] = False
 
-    def wgrad(self, wd, name):
-        """dW += conv weight gradient; tensor cores when the shape allows, FFMA otherwise."""
+    def wgrad(self, wd, name, keep=()):
+        """dW += conv weight gradient; tensor cores when the shape allows, FFMA otherwise.
+        A weight gradient is a LEAF of the backward pass (nothing downstream reads it before the optimizer), so
+        with ``wgrad_stream`` set (FusedTrainer does, around its step) it is forked onto that stream behind the
+        caller's current stream and the dgrad / norm-backward chain continues without it; ``join_wgrad()`` joins.
+        `keep`: the tensors the launch reads -- held until the join so that the caching allocator cannot hand their
+        memory to the launching stream while the forked kernel still reads them."""
+        ws = self.wgrad_stream
+        if ws is not None:
+            ws.wait_stream(torch.cuda.current_stream(self.dev))
+            self._wg_keep.extend(keep)
+            with torch.cuda.stream(ws):
+                self._wgrad_launch(wd, name)
+            return
+        self._wgrad_launch(wd, name)
+
+    def join_wgrad(self):
+        """The current stream waits for every forked weight gradient; releases the tensors held for them."""
+        if self.wgrad_stream is not None:
+            torch.cuda.current_stream(self.dev).wait_stream(self.wgrad_stream)
+        self._wg_keep.clear()
+
+    def _wgrad_launch(self, wd, name):
         if self.precision == "tf32":
             n = int(self.lib.avc_wgrad_tc_scratch_floats(C.byref(wd)))
             acc = self._wg_acc
@@ -491,7 +513,7 @@ class Engine:
         wd.B, wd.Cin, wd.Cout, wd.K, wd.stride, wd.pad_left, wd.Tin, wd.Tout = B, Cin, Cout, K, stride, rec["pl"], xin.T, Tout
         wd.x, wd.x_bstride, wd.dc, wd.dc_bstride = xin.ptr, xin.bstride, dc.ptr, dc.bstride
         wd.dw = G[name + ".weight"].data_ptr()
-        self.wgrad(wd, name)
+        self.wgrad(wd, name, keep=(xin.t, dc.t))
         if self.debug:
             self.debug(name, "dw", G[name + ".weight"])
         if not need_dx:
@@ -775,7 +797,7 @@ class Engine:
             wd.B, wd.Cin, wd.Cout, wd.K, wd.stride, wd.pad_left, wd.Tin, wd.Tout = x4.B, Cin, Cout, K, 1, pl, x4.T, Tout
             wd.x, wd.x_bstride, wd.dc, wd.dc_bstride = x4.ptr, x4.bstride, dci.ptr, dci.bstride
             wd.dw = G[name + ".weight"].data_ptr()
-            self.wgrad(wd, name)
+            self.wgrad(wd, name, keep=(x4.t, dbank.t))
 
     # ------------------------------------------------------------------ reparameterisation
     def reparam_fwd(self, mu4: A4, ls4: A4, eps: Optional[torch.Tensor], want_planar=True):

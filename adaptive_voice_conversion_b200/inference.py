@@ -9,6 +9,7 @@ the batched entry point BASELINE config 5 measures.
 """
 from __future__ import annotations
 
+import os
 import pickle
 
 import torch
@@ -55,8 +56,37 @@ class Inferencer(object):
 
     @torch.no_grad()
     def inference_batch(self, x, x_cond):
-        """x [B, n_mels, T], x_cond [B, n_mels, T_c] device tensors -> dec [B, n_mels, 8*ceil(T/8)]."""
-        return self.model.inference(x, x_cond)
+        """x [B, n_mels, T], x_cond [B, n_mels, T_c] device tensors -> dec [B, n_mels, 8*ceil(T/8)].
+
+        One conversion is ~150 dependent kernel launches of a few microseconds each -- issued one by one from Python
+        the GPU waits for the host.  The call is therefore captured ONCE per (shape, parameter version) into a CUDA
+        graph (the speaker / content branches on two streams, model.AE.inference) and replayed on static input
+        buffers; at most 8 shapes (serving buckets) are kept.  AVC_INFER_GRAPH=0: plain eager calls."""
+        if os.environ.get("AVC_INFER_GRAPH", "1") != "1" or not x.is_cuda:
+            return self.model.inference(x, x_cond)
+        key = (tuple(x.shape), tuple(x_cond.shape), str(x.device), self._param_version())
+        graphs = self.__dict__.setdefault("_graphs", {})
+        g = graphs.get(key)
+        if g is None:
+            if len(graphs) >= 8:
+                graphs.clear()
+            sx, sc = x.contiguous().clone(), x_cond.contiguous().clone()
+            self.model.inference(sx, sc)          # eager once: weight packs, allocator warm-up, argument checks
+            torch.cuda.synchronize(x.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.model.inference(sx, sc)
+            g = graphs[key] = (graph, sx, sc, out)
+        graph, sx, sc, out = g
+        sx.copy_(x, non_blocking=True)
+        sc.copy_(x_cond, non_blocking=True)
+        graph.replay()
+        return out.clone()
+
+    def _param_version(self):
+        # in-place updates (optimizer steps, load_state_dict) bump a tensor's version counter: a captured graph reads
+        # the weight packs of the version it was captured with
+        return sum(int(p._version) for p in self.model.parameters())
 
     @torch.no_grad()
     def inference_ragged(self, xs, x_conds):
@@ -75,7 +105,7 @@ class Inferencer(object):
         for (_, _), idx in sorted(buckets.items()):
             xb = torch.cat([self.utt_make_frames(xs[i]) for i in idx], dim=0)
             cb = torch.cat([self.utt_make_frames(x_conds[i]) for i in idx], dim=0)
-            dec = self.model.inference(xb, cb)               # [n, n_mels, 8*ceil(T/8)]
+            dec = self.inference_batch(xb, cb)               # [n, n_mels, 8*ceil(T/8)]
             for j, i in enumerate(idx):
                 out[i] = dec[j].transpose(0, 1)
         self.model.engine(xs[0].device).check_tc_status()

@@ -18,6 +18,8 @@ model on CPU tensors raises.
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, List, Optional
 
 import torch
@@ -253,9 +255,32 @@ class AE(nn.Module):
         x = _check_input(x, "AE.inference(x)")
         x_cond = _check_input(x_cond, "AE.inference(x_cond)")
         with torch.no_grad():
-            emb = _SpeakerFn.apply(self, x_cond, *self._params("speaker_encoder."))
+            side = self._side_stream(x.device)
+            if side is None:
+                emb = _SpeakerFn.apply(self, x_cond, *self._params("speaker_encoder."))
+                mu, log_sigma = _ContentFn.apply(self, x, *self._params("content_encoder."))
+                return _DecoderFn.apply(self, mu, log_sigma, None, emb, *self._params("decoder."))
+            # the speaker encoder (on x_cond) and the content encoder (on x) are independent until the decoder: the
+            # speaker branch runs on a second stream (fork / join), as in the fused train step (trainer.py)
+            main = torch.cuda.current_stream(x.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                emb = _SpeakerFn.apply(self, x_cond, *self._params("speaker_encoder."))
             mu, log_sigma = _ContentFn.apply(self, x, *self._params("content_encoder."))
+            main.wait_stream(side)
+            if not torch.cuda.is_current_stream_capturing():
+                emb.record_stream(main)   # allocated on the side stream, read by the decoder on this one
             return _DecoderFn.apply(self, mu, log_sigma, None, emb, *self._params("decoder."))
+
+    def _side_stream(self, dev):
+        if os.environ.get("AVC_OVERLAP", "1") != "1":
+            return None
+        st = getattr(self, "_side_streams", None)
+        if st is None:
+            st = self._side_streams = {}
+        if dev not in st:
+            st[dev] = torch.cuda.Stream(dev)
+        return st[dev]
 
     def get_speaker_embeddings(self, x: torch.Tensor):
         """AE.get_speaker_embeddings (model.py:393-395)."""

@@ -54,7 +54,15 @@ class FusedTrainer:
         self.eng.prepare_tables(self.P, self.G)   # before any CUDA-graph capture
         self.eng.prepare_wgrad_acc(self.P, self.G)
         self.overlap = os.environ.get("AVC_OVERLAP", "1") == "1"
-        self._side = torch.cuda.Stream(self.dev) if self.overlap else None
+        # Optional (AVC_WGRAD_STREAM=1; correct, measured SLOWER: 58.1k vs 60.1k seg/s): conv weight gradients are leaves
+        # of the backward pass and can fork onto their own stream -- but a weight-gradient kernel holds 128 SMs for
+        # ~20 us (one ~190 KB CTA per SM, like the conv kernel), and whenever it grabs them inside a bubble of the
+        # dgrad / norm-backward chain the next critical-path conv waits for it.  With the option the chains are
+        # captured on high-priority streams and the weight gradients on a normal-priority one.
+        wg = os.environ.get("AVC_WGRAD_STREAM", "0") == "1" and self.overlap
+        self._side = torch.cuda.Stream(self.dev, priority=-1 if wg else 0) if self.overlap else None
+        self._wgs = torch.cuda.Stream(self.dev, priority=0) if wg else None
+        self._cap = torch.cuda.Stream(self.dev, priority=-1) if wg else None   # capture stream of the graphs
         self._lambda_kl = None
         self._hp_key = None
         self._static_eps = None
@@ -88,6 +96,16 @@ class FusedTrainer:
                                       dls.data_ptr(), eng.stream), "vae_loss")
         ddec4 = A4.empty(dec4.B, dec4.C, dec4.T, self.dev)
         eng.pack_a4(ddec, ddec4)
+        eng.wgrad_stream = self._wgs
+        try:
+            return self._bwd(x, eps, mu, ls, emb, dec, ls4, dmu, dls, cs, ce, cd, ddec4)
+        finally:
+            eng.wgrad_stream = None
+            eng._wg_keep.clear()
+
+    def _bwd(self, x, eps, mu, ls, emb, dec, ls4, dmu, dls, cs, ce, cd, ddec4):
+        eng, P, G = self.eng, self.P, self.G
+        main, side = torch.cuda.current_stream(self.dev), self._side
         dz4, demb = eng.decoder_bwd(P, G, cd, ddec4)
         # ---- backward: the two encoders again in parallel (disjoint parameters, disjoint gradient buffers)
         if side is not None:
@@ -102,6 +120,7 @@ class FusedTrainer:
             eng.speaker_bwd(P, G, cs, demb)
         # (every tensor the side stream touched -- x, emb, demb, cs -- is a local that lives until this function
         # returns, i.e. until after the join: the caching allocator cannot hand its memory to the other stream early)
+        eng.join_wgrad()    # the forked weight gradients (of both branches) before their accumulators are flushed
         eng.flush_wgrad()   # no-op unless weight gradients were accumulated in place (AVC_WGRAD_ACC=1)
         return mu, ls, emb, dec
 
@@ -166,15 +185,15 @@ class FusedTrainer:
         ga = torch.cuda.CUDAGraph()
         pool = torch.cuda.graph_pool_handle()
         if self.world == 1:    # one process: the whole step (zero-grad .. weight re-pack) is ONE graph
-            with torch.cuda.graph(ga, pool=pool):
+            with torch.cuda.graph(ga, pool=pool, stream=self._cap):
                 self._fwd_bwd(self._static, self._static_eps)
                 self._update()
             self._graphs = (ga, None)
             return self._static
         gb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(ga, pool=pool):
+        with torch.cuda.graph(ga, pool=pool, stream=self._cap):
             self._fwd_bwd(self._static, self._static_eps)
-        with torch.cuda.graph(gb, pool=pool):
+        with torch.cuda.graph(gb, pool=pool, stream=self._cap):
             self._update()
         self._graphs = (ga, gb)
         return self._static

@@ -295,6 +295,32 @@ def test_inference_ragged_batch_equals_per_utterance(precision):
             assert relerr(outs[i].t()[None], ref) < tol(precision, REL, 8e-3), i
 
 
+def test_inference_graph_replay_equals_eager(monkeypatch):
+    """Inferencer.inference_batch replays a captured CUDA graph (two streams inside): a replay on NEW inputs equals
+    the eager call bit for bit (same kernels, same launch order per stream), and an in-place parameter update
+    invalidates the graph (the packs it reads belong to the old weights)."""
+    from adaptive_voice_conversion_b200.inference import Inferencer
+    cfg = orc.default_config(80)
+    args = types.SimpleNamespace(attr=None, model=None, source=None, target=None, output=None, sample_rate=24000)
+    inf = Inferencer(cfg, args)
+    inf.model.load_state_dict(orc.init_state(cfg, seed=0), strict=True)
+    mk = lambda seed, t: torch.randn((4, 80, t), generator=torch.Generator().manual_seed(seed)).cuda()
+    x0, c0, x1, c1 = mk(1, 128), mk(2, 96), mk(3, 128), mk(4, 96)
+    inf.inference_batch(x0, c0)                       # captures
+    got = inf.inference_batch(x1, c1)                 # replays on new inputs
+    assert len(inf._graphs) == 1
+    monkeypatch.setenv("AVC_INFER_GRAPH", "0")
+    want = inf.inference_batch(x1, c1)
+    assert torch.equal(got, want)
+    monkeypatch.setenv("AVC_INFER_GRAPH", "1")
+    with torch.no_grad():
+        inf.model.decoder.out_conv_layer.bias.add_(1.0)
+    got2 = inf.inference_batch(x1, c1)
+    assert len(inf._graphs) == 2
+    assert float((got2 - want - 1.0).abs().max()) < 1e-5
+    inf.model.engine(x0.device).check_tc_status()
+
+
 def test_inferencer_api(tmp_path, precision):
     from adaptive_voice_conversion_b200.inference import Inferencer
     cfg = orc.default_config(80)
