@@ -54,12 +54,15 @@ class FusedTrainer:
         self.eng.prepare_tables(self.P, self.G)   # before any CUDA-graph capture
         self.eng.prepare_wgrad_acc(self.P, self.G)
         self.overlap = os.environ.get("AVC_OVERLAP", "1") == "1"
-        # Optional (AVC_WGRAD_STREAM=1; correct, measured SLOWER: 58.1k vs 60.1k seg/s): conv weight gradients are leaves
-        # of the backward pass and can fork onto their own stream -- but a weight-gradient kernel holds 128 SMs for
-        # ~20 us (one ~190 KB CTA per SM, like the conv kernel), and whenever it grabs them inside a bubble of the
-        # dgrad / norm-backward chain the next critical-path conv waits for it.  With the option the chains are
-        # captured on high-priority streams and the weight gradients on a normal-priority one.
-        wg = os.environ.get("AVC_WGRAD_STREAM", "0") == "1" and self.overlap
+        # Conv weight gradients are leaves of the backward pass: they can fork onto their own (lower-priority) stream
+        # while the dgrad / norm-backward chain continues.  Measured (B=256): forking the DECODER's weight gradients
+        # only -- the phase in which ONE chain is active and SMs idle -- 60.1k -> 62.4k seg/s (AVC_WGRAD_STREAM=2,
+        # default); forking all of them 60.6k (=1): during the encoders' backward two chains are already active, and a
+        # weight-gradient kernel holds 128 SMs for ~20 us (one ~190 KB CTA per SM, like the conv kernel), so whenever it
+        # grabs them inside a bubble the next critical-path conv waits for it; =0: all in line.  The chains are captured
+        # on high-priority streams, the weight gradients on a normal-priority one.
+        self._wg_mode = os.environ.get("AVC_WGRAD_STREAM", "2")   # "1": every conv weight gradient, "2": the decoder's only
+        wg = self._wg_mode in ("1", "2") and self.overlap
         self._side = torch.cuda.Stream(self.dev, priority=-1 if wg else 0) if self.overlap else None
         self._wgs = torch.cuda.Stream(self.dev, priority=0) if wg else None
         self._cap = torch.cuda.Stream(self.dev, priority=-1) if wg else None   # capture stream of the graphs
@@ -107,6 +110,8 @@ class FusedTrainer:
         eng, P, G = self.eng, self.P, self.G
         main, side = torch.cuda.current_stream(self.dev), self._side
         dz4, demb = eng.decoder_bwd(P, G, cd, ddec4)
+        if self._wg_mode == "2":
+            eng.wgrad_stream = None      # only the decoder's weight gradients fork (one chain active: idle SMs to fill)
         # ---- backward: the two encoders again in parallel (disjoint parameters, disjoint gradient buffers)
         if side is not None:
             side.wait_stream(main)
@@ -120,6 +125,7 @@ class FusedTrainer:
             eng.speaker_bwd(P, G, cs, demb)
         # (every tensor the side stream touched -- x, emb, demb, cs -- is a local that lives until this function
         # returns, i.e. until after the join: the caching allocator cannot hand its memory to the other stream early)
+        eng.wgrad_stream = self._wgs
         eng.join_wgrad()    # the forked weight gradients (of both branches) before their accumulators are flushed
         eng.flush_wgrad()   # no-op unless weight gradients were accumulated in place (AVC_WGRAD_ACC=1)
         return mu, ls, emb, dec
