@@ -816,16 +816,16 @@ class Engine:
         return dmu4, dls4
 
     # ------------------------------------------------------------------ decoder
-    def decoder_fwd(self, P, z4: A4, emb: torch.Tensor, train: bool):
-        """Decoder.forward (model.py:347-371) -> dec4 A4 [B, c_out, 8*T]."""
+    def decoder_affine_fwd(self, P, emb: torch.Tensor, train: bool):
+        """The 2*n AdaIN rows (beta|gamma) of every decoder block: conv_affine_layers (model.py:342-343, used :356,:363).
+        They read the speaker embedding only, so a caller that runs the speaker encoder on its own stream computes
+        them there (trainer.py) and hands the result to decoder_fwd.  -> (conds [B, 2n, 2*c_h], aff)"""
         c = self.cfg["Decoder"]
         dn = "decoder"
-        ctx: dict = {}
-        out, r_in = self.conv(P, f"{dn}.in_conv_layer", z4, norm=True, relu=True, train=train)
         nblk = c["n_conv_blocks"]
-        # the 2*n AdaIN rows (beta|gamma) of every block: conv_affine_layers (model.py:342-343)
         ch2 = 2 * c["c_h"]
-        conds = self.empty(z4.B, 2 * nblk, ch2)
+        B = emb.shape[0]
+        conds = self.empty(B, 2 * nblk, ch2)
         aff = []
         naff = 2 * nblk
         fused_aff = self.fused_dense and naff <= L.LINEAR_BATCH_MAX and emb.is_contiguous()
@@ -833,7 +833,7 @@ class Engine:
             anames = self._affine_names(dn)
             tab = self._param_table("params", anames, P)
             bd = L.LinearBatchDesc()
-            bd.L, bd.B, bd.N, bd.K = naff, z4.B, ch2, emb.shape[1]
+            bd.L, bd.B, bd.N, bd.K = naff, B, ch2, emb.shape[1]
             bd.params, bd.x, bd.x_bstride = tab.data_ptr(), emb.data_ptr(), emb.stride(0)
             bd.out, bd.y_bstride = conds.data_ptr(), naff * ch2
             for i in range(naff):
@@ -844,6 +844,17 @@ class Engine:
             for i in range(naff):
                 _, r = self.linear(P, f"{dn}.conv_affine_layers.{i}", emb, out=conds[:, i], train=train)
                 aff.append(r)
+        return conds, aff
+
+    def decoder_fwd(self, P, z4: A4, emb: torch.Tensor, train: bool, affine=None):
+        """Decoder.forward (model.py:347-371) -> dec4 A4 [B, c_out, 8*T].  affine: the result of decoder_affine_fwd
+        when the caller already computed it (on the speaker branch's stream)."""
+        c = self.cfg["Decoder"]
+        dn = "decoder"
+        ctx: dict = {}
+        out, r_in = self.conv(P, f"{dn}.in_conv_layer", z4, norm=True, relu=True, train=train)
+        nblk = c["n_conv_blocks"]
+        conds, aff = affine if affine is not None else self.decoder_affine_fwd(P, emb, train)
         blocks = []
         for l, up in enumerate(c["upsample"][:nblk]):
             y, r1 = self.conv(P, f"{dn}.first_conv_layers.{l}", out, norm=True, cond=conds[:, 2 * l], relu=True, train=train,
@@ -857,8 +868,11 @@ class Engine:
             ctx.update(in_rec=r_in, aff=aff, blocks=blocks, out_rec=r_out, conds=conds, emb=emb)
         return dec4, ctx
 
-    def decoder_bwd(self, P, G, ctx, ddec4: A4, need_dz=True):
-        """Returns (dz4, demb)."""
+    def decoder_bwd(self, P, G, ctx, ddec4: A4, need_dz=True, affine_stream=None):
+        """Returns (dz4, demb).  affine_stream: the gradients of the AdaIN affine layers (and demb, which only the
+        speaker encoder's backward needs) are complete after the block loop; with a stream given they fork onto it
+        there, beside the in_conv data gradient -- demb is then produced ON that stream (the caller continues the
+        speaker branch on it) and the tensors the forked launches read stay alive in ctx."""
         c = self.cfg["Decoder"]
         nblk = c["n_conv_blocks"]
         dout = self.conv_bwd(P, G, ctx["out_rec"], ddec4)
@@ -876,7 +890,17 @@ class Engine:
             dout = self.conv_bwd(P, G, r1, dy1, dc_pre=f1["dc"], dres=dout, dres_mode=L.RES_UP if up > 1 else L.RES_SAME,
                                  dcond=dconds[:, 2 * l], fuse_up=f2)
             dc2 = f2["dc"]
+        if affine_stream is not None:
+            affine_stream.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(affine_stream):
+                demb = self._decoder_affine_bwd(P, G, ctx, dconds)
+            ctx["_keep_bwd"] = (dconds,)
+            dz4 = self.conv_bwd(P, G, ctx["in_rec"], dout, dc_pre=dc2, need_dx=need_dz)
+            return dz4, demb
         dz4 = self.conv_bwd(P, G, ctx["in_rec"], dout, dc_pre=dc2, need_dx=need_dz)
+        return dz4, self._decoder_affine_bwd(P, G, ctx, dconds)
+
+    def _decoder_affine_bwd(self, P, G, ctx, dconds):
         demb = None
         aff = ctx["aff"]
         if isinstance(aff, dict):   # the 2n affine layers in three launches
@@ -897,4 +921,4 @@ class Engine:
         else:
             for i, r in enumerate(aff):
                 demb = self.linear_bwd(P, G, r, dconds[:, i], dx_add=demb)
-        return dz4, demb
+        return demb

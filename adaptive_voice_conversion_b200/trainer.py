@@ -82,15 +82,17 @@ class FusedTrainer:
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 emb, cs = eng.speaker_fwd(P, x, True)
+                aff = eng.decoder_affine_fwd(P, emb, True)   # the AdaIN rows need the speaker embedding only
         else:
             emb, cs = eng.speaker_fwd(P, x, True)
+            aff = None
         mu4, ls4, ce = eng.content_fwd(P, x, True)
         if eps is None:
             eps = torch.randn((mu4.B, mu4.C, mu4.T), dtype=torch.float32, device=self.dev)
         mu, ls, z4 = eng.reparam_fwd(mu4, ls4, eps)
         if side is not None:
             main.wait_stream(side)
-        dec4, cd = eng.decoder_fwd(P, z4, emb, True)
+        dec4, cd = eng.decoder_fwd(P, z4, emb, True, affine=aff)
         dec = eng.unpack_a4(dec4)
         ddec, dmu, dls = torch.empty_like(dec), torch.empty_like(mu), torch.empty_like(ls)
         self.n_rec, self.n_lat = dec.numel(), mu.numel()
@@ -109,12 +111,13 @@ class FusedTrainer:
     def _bwd(self, x, eps, mu, ls, emb, dec, ls4, dmu, dls, cs, ce, cd, ddec4):
         eng, P, G = self.eng, self.P, self.G
         main, side = torch.cuda.current_stream(self.dev), self._side
-        dz4, demb = eng.decoder_bwd(P, G, cd, ddec4)
+        # the affine-layer gradients and demb fork onto the side stream after the decoder's block loop, beside its in_conv
+        dz4, demb = eng.decoder_bwd(P, G, cd, ddec4, affine_stream=side)
         if self._wg_mode == "2":
             eng.wgrad_stream = None      # only the decoder's weight gradients fork (one chain active: idle SMs to fill)
-        # ---- backward: the two encoders again in parallel (disjoint parameters, disjoint gradient buffers)
+        # ---- backward: the two encoders again in parallel (disjoint parameters, disjoint gradient buffers); the speaker
+        # branch follows demb on the side stream without waiting for the rest of the main chain
         if side is not None:
-            side.wait_stream(main)
             with torch.cuda.stream(side):
                 eng.speaker_bwd(P, G, cs, demb)
         dmu4, dls4 = eng.reparam_bwd(dz4, ls4, eps, dmu, dls)
