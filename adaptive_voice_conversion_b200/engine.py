@@ -397,14 +397,31 @@ class Engine:
             it.Cout, it.Cin, it.K = Cout, Cin, K
             dw_ptr[n] = it.dw
         raw = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8).to(self.dev)
-        self._wg_acc = dict(key=key, arena=arena, offs=offs, dw_ptr=dw_ptr, items=raw, n=len(rows), max_units=max_units, dirty=False)
+        n_dec = sum(1 for r in rows if r[0].startswith("decoder."))
+        if n_dec and not all(r[0].startswith("decoder.") for r in rows[len(rows) - n_dec:]):
+            n_dec = 0   # (conv_names lists the decoder last; anything else: no partial flush)
+        self._wg_acc = dict(key=key, arena=arena, offs=offs, dw_ptr=dw_ptr, items=raw, n=len(rows), max_units=max_units, dirty=False,
+                            n_dec=n_dec, dec_done=False)
 
-    def flush_wgrad(self):
-        """Fold the accumulated conv weight gradients into the registered gradient buffers."""
+    def flush_wgrad(self, decoder_only=False):
+        """Fold the accumulated conv weight gradients into the registered gradient buffers.  decoder_only: just the
+        decoder's layers (the last rows of the item table) -- they are final as soon as the decoder's backward is, so
+        the trainer folds them on the weight-gradient stream while the encoders' backward runs; the closing call then
+        covers the remaining rows."""
         acc = self._wg_acc
-        if acc is not None and acc["dirty"]:
-            self._ck(self.lib.avc_wgrad_acc_flush(acc["items"].data_ptr(), acc["n"], acc["max_units"], self.stream), "wgrad_acc_flush")
-            acc["dirty"] = False
+        if acc is None or not acc["dirty"]:
+            return
+        n, nd = acc["n"], acc["n_dec"]
+        item = C.sizeof(L.WgradAccItem)
+        if decoder_only:
+            if nd > 0 and not acc["dec_done"]:
+                self._ck(self.lib.avc_wgrad_acc_flush(acc["items"].data_ptr() + (n - nd) * item, nd, acc["max_units"], self.stream), "wgrad_acc_flush[decoder]")
+                acc["dec_done"] = True
+            return
+        rows = n - nd if acc["dec_done"] else n
+        if rows > 0:
+            self._ck(self.lib.avc_wgrad_acc_flush(acc["items"].data_ptr(), rows, acc["max_units"], self.stream), "wgrad_acc_flush")
+        acc["dirty"], acc["dec_done"] = False, False
 
     def wgrad(self, wd, name, keep=()):
         """dW += conv weight gradient; tensor cores when the shape allows, FFMA otherwise.

@@ -115,6 +115,9 @@ class FusedTrainer:
         dz4, demb = eng.decoder_bwd(P, G, cd, ddec4, affine_stream=side)
         if self._wg_mode == "2":
             eng.wgrad_stream = None      # only the decoder's weight gradients fork (one chain active: idle SMs to fill)
+            if self._wgs is not None:
+                with torch.cuda.stream(self._wgs):
+                    eng.flush_wgrad(decoder_only=True)   # ... and are folded into the gradient buffer there, behind them
         # ---- backward: the two encoders again in parallel (disjoint parameters, disjoint gradient buffers); the speaker
         # branch follows demb on the side stream without waiting for the rest of the main chain
         if side is not None:
