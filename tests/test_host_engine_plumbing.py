@@ -115,6 +115,49 @@ def test_wgrad_accumulation_bookkeeping(rig):
     assert e._wg_acc is None
 
 
+def test_decoder_accumulators_can_be_flushed_early(rig):
+    """flush_wgrad(decoder_only=True) covers exactly the decoder's rows (the tail of the item table), the closing
+    flush the rest; nothing is flushed twice and the flags reset for the next step (trainer.py: the decoder's weight
+    gradients are folded on their own stream while the encoders' backward runs)."""
+    e, P, G = rig
+    e.wgrad_acc = True
+    e.prepare_wgrad_acc(P, G)
+    acc = e._wg_acc
+    n_dec = sum(1 for n in e.conv_names() if n.startswith("decoder."))
+    assert acc["n_dec"] == n_dec == 14
+    seen = []
+    real = e.lib.__getattr__("avc_wgrad_acc_flush")
+
+    def flush(items, n, max_units, stream):
+        seen.append((items - acc["items"].data_ptr(), n))
+        return real(items, n, max_units, stream)
+    e.lib.__dict__["avc_wgrad_acc_flush"] = flush
+    from adaptive_voice_conversion_b200.engine import A4
+    for _ in range(2):                                   # two steps: the flags must reset
+        seen.clear()
+        x = torch.randn(4, 80, 128)
+        emb, cs = e.speaker_fwd(P, x, True)
+        mu4, ls4, ce = e.content_fwd(P, x, True)
+        eps = torch.randn(4, 128, 16)
+        mu, ls, z4 = e.reparam_fwd(mu4, ls4, eps)
+        dec4, cd = e.decoder_fwd(P, z4, emb, True, affine=e.decoder_affine_fwd(P, emb, True))
+        dz4, demb = e.decoder_bwd(P, G, cd, A4.empty(dec4.B, dec4.C, dec4.T, e.dev))
+        e.flush_wgrad(decoder_only=True)
+        e.flush_wgrad(decoder_only=True)                 # idempotent
+        dmu4, dls4 = e.reparam_bwd(dz4, ls4, eps, torch.zeros_like(mu), torch.zeros_like(ls))
+        e.content_bwd(P, G, ce, dmu4, dls4)
+        e.speaker_bwd(P, G, cs, demb)
+        e.join_wgrad()
+        e.flush_wgrad()
+        item = 32                                        # sizeof(avc_wgrad_acc_item)
+        assert seen == [((58 - n_dec) * item, n_dec), (0, 58 - n_dec)]
+        assert not acc["dirty"] and not acc["dec_done"]
+    # without the early call the closing flush takes every row
+    seen.clear()
+    full_step(e, P, G)
+    assert seen == [(0, 58)]
+
+
 def test_runtime_options_roundtrip():
     from adaptive_voice_conversion_b200 import _lib as L
     for name in ("tc_uniform_issue", "wgrad_reduce_v2"):
