@@ -306,6 +306,7 @@ def test_inference_graph_replay_equals_eager(monkeypatch):
     inf.model.load_state_dict(orc.init_state(cfg, seed=0), strict=True)
     mk = lambda seed, t: torch.randn((4, 80, t), generator=torch.Generator().manual_seed(seed)).cuda()
     x0, c0, x1, c1 = mk(1, 128), mk(2, 96), mk(3, 128), mk(4, 96)
+    monkeypatch.setenv("AVC_INFER_GRAPH", "1")        # (the suite may run with the switch off)
     inf.inference_batch(x0, c0)                       # captures
     got = inf.inference_batch(x1, c1)                 # replays on new inputs
     assert len(inf._graphs) == 1
