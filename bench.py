@@ -76,7 +76,9 @@ def workload_config(args, world):
     """`config` of the JSON line -- the same dict on the product arm and on the reference arm."""
     B = args.batch
     return {"workload": f"Solver.ae_step fwd+bwd+clip+Adam(amsgrad), batch {B}/GPU of {args.c_in}-mel x 128-frame segments (BASELINE config 3/4)",
-            "global_batch": B * world, "per_gpu_batch": B, "c_in": args.c_in, "parallelism": f"dp{world}"}
+            "global_batch": B * world, "per_gpu_batch": B, "c_in": args.c_in, "parallelism": f"dp{world}",
+            # timing rule: inputs / working set larger than L2 (a property of the workload, the same on both arms)
+            "l2": "per-step working set (~1.5 GB saved activations at batch 256) >> 126 MB L2; no explicit flush"}
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -193,7 +195,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": spt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic N(0,1) segments, random-init weights (seed 0)",
-        "config": dict(workload_config(args, max(1, args.gpus)), executed_on="host CPU (reference arm)"),
+        "config": workload_config(args, max(1, args.gpus)),   # identical to the product arm's
+        "run": {"executed_on": "host CPU (reference arm: the oracle port of the reference's Solver.ae_step)"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{steps} steps of one GPU's batch ({sample_b} segments) after {warmup} warm-up (oracle port of the reference Solver.ae_step, torch CPU fp32, best of a thread sweep: {cores} of {os.cpu_count()} threads)"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -382,10 +385,10 @@ def run_b200(args):
             # arithmetic type of the conv path: tcgen05 kind::tf32 (TF32 operands, fp32 accumulate) or exact fp32 FFMA
             "dtype": "tf32" if precision == "tf32" else "f32",
             "data": "synthetic N(0,1) segments, random-init weights",
-            "config": dict(workload_config(args, world), cuda_graph=not args.no_graph,
-                           streams="2 (speaker-encoder branch forked beside the content-encoder branch, forward and backward)"
-                           if os.environ.get("AVC_OVERLAP", "1") == "1" else "1",
-                           l2="per-step working set (~1.5 GB saved activations) >> 126 MB L2; no explicit flush"),
+            "config": workload_config(args, world),   # identical on the reference arm
+            "run": {"executed_on": "B200", "cuda_graph": not args.no_graph,
+                    "streams": ("3 (speaker-encoder branch beside the content-encoder branch, forward and backward; the decoder's weight "
+                                "gradients on a third, lower-priority stream)") if os.environ.get("AVC_OVERLAP", "1") == "1" else "1"},
             "timing": {"windows": NWIN, "steps_per_window": K, "reported": "median window",
                        "window_ms": win, "e2e_window_ms": win_e2e},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": B * args.c_in * SEG_T * 4, "d2h_bytes_per_step": 16,
