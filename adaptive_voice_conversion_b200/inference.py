@@ -74,7 +74,7 @@ class Inferencer(object):
             self.model.inference(sx, sc)          # eager once: weight packs, allocator warm-up, argument checks
             torch.cuda.synchronize(x.device)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 out = self.model.inference(sx, sc)
             g = graphs[key] = (graph, sx, sc, out)
         graph, sx, sc, out = g

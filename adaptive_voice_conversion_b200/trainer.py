@@ -49,6 +49,10 @@ class FusedTrainer:
         self.n_lat = 1
         self._graphs = None
         self._static = None
+        # the third consecutive step on the same batch shape (no injected eps) is recorded into CUDA graphs and every
+        # later one replays them: a plain `Solver.train` loop gets the graph path without calling capture() (AVC_GRAPH=0: eager)
+        self.auto_graph = os.environ.get("AVC_GRAPH", "1") == "1"
+        self._eager_shape, self._eager_n = None, 0
         self.launches_per_step = 0
         self.eng.pack_weights(self.P, need_dgrad=True)
         self.eng.prepare_tables(self.P, self.G)   # before any CUDA-graph capture
@@ -168,11 +172,16 @@ class FusedTrainer:
                 self._static.copy_(x, non_blocking=True)
             if eps is not None and eps.data_ptr() != self._static_eps.data_ptr():
                 self._static_eps.copy_(eps, non_blocking=True)
-            self._graphs[0].replay()
-            if self._graphs[1] is not None:   # N > 1: the NCCL all-reduce sits between the two graphs
-                self._allreduce()
-                self._graphs[1].replay()
+            self._replay()
             return None
+        if self.auto_graph and self._graphs is None and eps is None and not return_outputs:
+            shp = tuple(x.shape)
+            self._eager_n = self._eager_n + 1 if shp == self._eager_shape else 1
+            self._eager_shape = shp
+            if self._eager_n > 2:          # two eager steps of this shape are behind us (allocator, tables, packs warm)
+                self.capture(x, warmup=0)  # records only; `_static` is a copy of x
+                self._replay()             # ... and this is the step itself
+                return None
         n0 = L.launch_count()
         outs = self._fwd_bwd(x, eps)
         self._allreduce()
@@ -180,11 +189,19 @@ class FusedTrainer:
         self.launches_per_step = L.launch_count() - n0
         return outs if return_outputs else None
 
+    def _replay(self):
+        self._graphs[0].replay()
+        if self._graphs[1] is not None:   # N > 1: the NCCL all-reduce sits between the two graphs
+            self._allreduce()
+            self._graphs[1].replay()
+
     def capture(self, x_example: torch.Tensor, warmup: int = 2, eps_example: Optional[torch.Tensor] = None):
         """Capture the step for x_example's shape into CUDA graphs.  Runs `warmup` real
         (eager) steps first -- they DO update the parameters.  With eps_example the graph reads the
         reparameterisation noise from a static buffer that step(x, lambda_kl, eps=...) refills (parity
-        tests inject eps); without it eps is drawn inside the graph from torch's device generator."""
+        tests inject eps); without it eps is drawn inside the graph from torch's device generator.
+        (capture_error_mode="thread_local": a DataLoader's pin-memory thread may allocate pinned memory while this
+        thread records.)"""
         lam = self._lambda_kl if self._lambda_kl is not None else float(self.cfg["lambda"]["lambda_kl"])
         self.eng.prepare_tables(self.P, self.G)
         self.eng.prepare_wgrad_acc(self.P, self.G)
@@ -197,15 +214,15 @@ class FusedTrainer:
         ga = torch.cuda.CUDAGraph()
         pool = torch.cuda.graph_pool_handle()
         if self.world == 1:    # one process: the whole step (zero-grad .. weight re-pack) is ONE graph
-            with torch.cuda.graph(ga, pool=pool, stream=self._cap):
+            with torch.cuda.graph(ga, pool=pool, stream=self._cap, capture_error_mode="thread_local"):
                 self._fwd_bwd(self._static, self._static_eps)
                 self._update()
             self._graphs = (ga, None)
             return self._static
         gb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(ga, pool=pool, stream=self._cap):
+        with torch.cuda.graph(ga, pool=pool, stream=self._cap, capture_error_mode="thread_local"):
             self._fwd_bwd(self._static, self._static_eps)
-        with torch.cuda.graph(gb, pool=pool, stream=self._cap):
+        with torch.cuda.graph(gb, pool=pool, stream=self._cap, capture_error_mode="thread_local"):
             self._update()
         self._graphs = (ga, gb)
         return self._static

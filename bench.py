@@ -329,6 +329,7 @@ def run_b200(args):
 
     # ---- device-resident arm: NWIN windows of exactly K steps, each bracketed by barrier + synchronize; the
     # reported window is the MEDIAN one (a single 0.1 s window is at the mercy of one straggler rank)
+    tr.auto_graph = False            # the capture below is explicit; --no-graph (profiling runs) stays eager
     if not args.no_graph:
         tr.capture(x_dev, warmup=2)
     for _ in range(W):

@@ -245,6 +245,35 @@ def test_graph_step_matches_eager(tmp_path):
         assert rel_l2(p1, p0) < (1e-3 if i == 0 else 5e-3), (i, rel_l2(p1, p0))
 
 
+def test_plain_training_loop_gets_the_graph_path(tmp_path, monkeypatch):
+    """Solver.ae_step in a plain loop (what train.sh runs): the third step on the same batch shape is recorded into
+    CUDA graphs and later ones replay them; a different batch shape falls back to eager launches without dropping the
+    graphs; AVC_GRAPH=0 keeps everything eager."""
+    from adaptive_voice_conversion_b200.solver import Solver
+    cfg = orc.default_config(80)
+    cfg["data_loader"]["batch_size"] = 8
+    monkeypatch.setenv("AVC_GRAPH", "1")
+    solver = Solver(cfg, _solver_args(tmp_path))
+    tr = solver.trainer
+    x = torch.randn((8, 80, 128), generator=torch.Generator().manual_seed(1))
+    seen = []
+    for i in range(5):
+        meta = solver.ae_step(x, 1.0)
+        seen.append(tr._graphs is not None)
+        assert all(v == v and abs(v) < 1e4 for v in meta.values()), meta      # finite
+    assert seen == [False, False, True, True, True]
+    assert meta["loss_rec"] < 1.5
+    solver.ae_step(x[:4], 1.0)                                                  # odd batch: eager, graphs kept
+    assert tr._graphs is not None and tuple(tr._static.shape) == (8, 80, 128)
+    solver.ae_step(x, 1.0)
+    tr.eng.check_tc_status()
+    monkeypatch.setenv("AVC_GRAPH", "0")
+    s2 = Solver(cfg, _solver_args(tmp_path))
+    for i in range(4):
+        s2.ae_step(x, 1.0)
+    assert s2.trainer._graphs is None
+
+
 def test_resume_restores_the_annealing_position(tmp_path):
     """save_model writes <path>.iter next to the reference-format .ckpt/.opt; a new Solver with load_model
     continues the KL annealing where the first one stopped (the reference restarts it, solver.py:100-104)."""
